@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — decode tokens/s, Llama-2-7B-shaped Q4_K_M GGUF, batch 1 (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one single-token decode pass of the whole hot path (160 weight mat-vecs + attention at a context of
+256..511 tokens).  Workload: synthetic 7B-shaped model (random valid quant blocks in the reference's Q4_K_M tensor mix,
+3.8 GB of weights ≫ the 126 MB L2, so every step streams its inputs from HBM — no L2 flush needed), 256-token prompt
+prefilled untimed, then W warm-up + K timed decode steps.
+
+  value     device-timed: K steps replayed as CUDA graphs with the token fed back on the device (k_argmax), CUDA events on the
+            launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling)
+  e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, logits D2H and the
+            host sampler inside the timed region
+  roofline  HBM: algorithmic weight+KV bytes per step ÷ step time, against MEASURED_PEAKS.json hbm_gbs; plus the mat-vec
+            kernels alone from an eager pass with a CUDA event after every kernel
+  cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref/libctransformers_ref.so) on the host cores, same
+            model file, same prompt, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CTX = 512
+PROMPT = 256
+MODEL_DIR = Path(os.environ.get("CTB_MODEL_DIR", "/tmp/ctb_models"))
+REF_SO = ROOT / "oracle" / "_ref" / "libctransformers_ref.so"
+
+
+def model_path():
+    return MODEL_DIR / "llama2-7b-shaped.Q4_K_M.synthetic.gguf"
+
+
+def ensure_model(rank, world, barrier):
+    from ctransformers_b200 import synth
+    p = model_path()
+    if rank == 0 and not p.exists():
+        MODEL_DIR.mkdir(parents=True, exist_ok=True)
+        tmp = p.with_suffix(".tmp")
+        synth.write_llama(tmp, synth.LLAMA2_7B, "Q4_K_M", seed=0)
+        tmp.rename(p)
+    barrier()
+    return p
+
+
+def prompt_ids():
+    import numpy as np
+    ids = np.random.default_rng(1).integers(259, 32000, PROMPT).tolist()
+    ids[0] = 1
+    return ids
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def kv_bytes_per_step(n_layer, n_embd_gqa, t_avg):
+    return 2 * n_layer * n_embd_gqa * t_avg * 2 + 2 * n_layer * n_embd_gqa * 2
+
+
+def run_reference(args, rank, world, barrier):
+    """The reference's own CPU implementation on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    if not REF_SO.exists():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libctransformers_ref.so was not built (needs /root/reference at build time)"}))
+        return
+    from ctransformers_b200 import AutoModelForCausalLM
+    cores = os.cpu_count() or 1
+    threads = max(1, min(cores, int(os.environ.get("CTB_REF_THREADS", cores))))
+    p = ensure_model(0, 1, lambda: None)
+    llm = AutoModelForCausalLM.from_pretrained(str(p), lib=str(REF_SO), context_length=CTX, threads=threads)
+    ids = prompt_ids()
+    llm.eval(ids, batch_size=256)           # untimed prefill, one chunk
+    tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 1))
+    for _ in range(args.warmup):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "decode tokens/s Llama-2-7B Q4_K_M b=1", "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "q4_K/q6_K x q8_K (int8 dot, fp32 combine)",
+        "data": "synthetic", "config": workload_config(1),
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "reference", "sample": f"{steps} decode steps at context {PROMPT}+ after a {PROMPT}-token prompt, llm.eval+llm.sample, {threads} threads"},
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": "Llama-2-7B-shaped Q4_K_M GGUF (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode",
+            "global_batch": n, "ctx": CTX, "prompt": PROMPT, "parallelism": f"replicas x{n} (one sequence per GPU, no collective)",
+            "l2": "inputs (3.8 GB weights/step) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=192)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dist = None
+    if args.impl == "reference":
+        return run_reference(args, rank, world, lambda: None)
+
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    from ctransformers_b200 import AutoModelForCausalLM, synth
+    path = ensure_model(rank, world, barrier)
+    llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=CTX)
+    shape = synth.LLAMA2_7B
+    ids = prompt_ids()
+    steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 1))
+    W = max(args.warmup, 3)
+
+    def prefill():
+        llm._context = []
+        llm.eval(ids, batch_size=256)
+        return llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+
+    # ------------------------------------------------------------------ device-timed ("value")
+    first = prefill()
+    out = (C.c_int * (W + steps))()
+    assert llm.ctb_llm_decode_greedy(first, PROMPT, W, out) >= 0                      # warm-up steps at n_past = 256..
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = llm.ctb_llm_decode_greedy(int(out[W - 1]), PROMPT + W, steps, out)           # K timed steps, CUDA events inside
+    barrier()
+    clocks = sampler.summary()
+    assert ms > 0
+    ms = max_over_ranks(ms)
+    tokens_dev = list(out[:steps])
+    value = world * steps / (ms / 1e3)
+
+    # ------------------------------------------------------------------ end to end through the public API ("e2e")
+    tok = prefill()
+    for _ in range(W):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_tokens = []
+    for _ in range(steps):
+        llm.eval([tok])                                   # H2D {token, n_past}; D2H logits + hidden state; stream sync
+        tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        e2e_tokens.append(tok)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = world * steps / e2e_s
+
+    # ------------------------------------------------------------------ roofline
+    peak, peak_src = hbm_peak()
+    wbytes = int(llm.ctb_llm_weight_bytes_per_token())
+    t_avg = PROMPT + W + steps / 2
+    gqa = shape.n_embd // shape.n_head * shape.n_head_kv
+    step_bytes = wbytes + kv_bytes_per_step(shape.n_layer, gqa, t_avg) + shape.n_vocab * 4
+    achieved = step_bytes / (ms / 1e3 / steps) / 1e9
+    ms_kind = (C.c_double * 4)()
+    cnt_kind = (C.c_int * 4)()
+    prof_steps = 4
+    for i in range(prof_steps):
+        llm.ctb_llm_profile_step(tokens_dev[i], PROMPT + W + steps // 2 + i - prof_steps, ms_kind, cnt_kind)
+    mv_ms_per_step = ms_kind[0] / prof_steps
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src, "bytes_per_step": step_bytes, "weight_bytes_per_step": wbytes,
+        "frac_vs_3.9GB_weights_only": (3.9e9 / (ms / 1e3 / steps) / 1e9) / peak,
+        "kernel": "k_matvec (quantized mat-vec; all %d launches of a step)" % (cnt_kind[0] // prof_steps),
+        "kernel_only": {"achieved": wbytes / (mv_ms_per_step / 1e3) / 1e9 if mv_ms_per_step > 0 else None,
+                        "frac": (wbytes / (mv_ms_per_step / 1e3) / 1e9) / peak if mv_ms_per_step > 0 else None,
+                        "ms_per_step": {"matvec": ms_kind[0] / prof_steps, "attention": ms_kind[1] / prof_steps, "rope_kv": ms_kind[2] / prof_steps, "other": ms_kind[3] / prof_steps},
+                        "how": f"eager pass, CUDA event after every kernel, {prof_steps} steps"},
+    }
+
+    result = {
+        "metric": "decode tokens/s Llama-2-7B Q4_K_M b=1", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": W,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "q4_K/q6_K x q8_K (int8 dp4a dot, fp32 combine)", "data": "synthetic", "config": workload_config(world),
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": shape.n_vocab * 4 + shape.n_embd * 4,
+                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs"},
+        "gpu_launches": int(llm.ctb_llm_launches_per_token()) * steps,
+        "roofline": roofline,
+        "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps],
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and REF_SO.exists():
+        del llm
+        cores = os.cpu_count() or 1
+        ref = AutoModelForCausalLM.from_pretrained(str(path), lib=str(REF_SO), context_length=CTX, threads=cores)
+        n_prompt, n_dec = 32, 12
+        ref.eval(ids[:n_prompt], batch_size=32)
+        t = ref.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        ref.eval([t])
+        t0 = time.perf_counter()
+        for _ in range(n_dec):
+            t = ref.sample(top_k=1, repetition_penalty=1.0, seed=0)
+            ref.eval([t])
+        dt = time.perf_counter() - t0
+        result["cpu_baseline"] = {"value": n_dec / dt, "unit": "tokens/s", "cores": cores, "kind": "reference",
+                                  "sample": f"{n_dec} decode steps after a {n_prompt}-token prompt (context ≈{n_prompt + n_dec}), same model file, unmodified reference CPU build (AVX2), {cores} threads"}
+    if rank == 0:
+        print(json.dumps(result))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

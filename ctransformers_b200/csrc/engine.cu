@@ -1,0 +1,526 @@
+// See engine.cuh.  Model upload (GGUF blocks → device planes), tables, KV cache, op schedule, CUDA graphs.
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "attention.cuh"
+#include "matvec.cuh"
+#include "repack.cuh"
+
+namespace ctb {
+
+#define CTB_CUDA(expr)                                                                                         \
+  do {                                                                                                         \
+    cudaError_t e__ = (expr);                                                                                  \
+    if (e__ != cudaSuccess)                                                                                    \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
+                               std::to_string(__LINE__) + " (" #expr ")");                                     \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// advance the on-device decode state after a greedy pick: state = {token, n_past, step}
+__global__ void k_advance(const int* pick, int* state, int* out_tokens) {
+  const int t = *pick;
+  out_tokens[state[2]] = t;
+  state[0] = t;
+  state[1] += 1;
+  state[2] += 1;
+}
+
+static bool supported_matrix_type(uint32_t t) {
+  return t == T_F32 || t == T_F16 || t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_K || t == T_Q5_K || t == T_Q6_K;
+}
+
+static size_t max_raw_tensor_bytes(const GGUFFile& g) {
+  size_t m = 0;
+  for (const auto& t : g.tensors) m = std::max(m, (size_t)t.nbytes);
+  return m;
+}
+
+size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
+  size_t total = 0;
+  for (const auto& t : g.tensors) total += align_up(t.nbytes, 256) + 4 * 256;   // up to 4 planes, each 256-aligned
+  total += align_up(max_raw_tensor_bytes(g), 256);                              // raw staging for the repack
+  const size_t kv = (size_t)hp.n_layer * hp.n_ctx * hp.n_embd_gqa() * 2;
+  total += 2 * align_up(kv, 256);
+  total += 3 * align_up(65536 * 2, 256);
+  total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
+  const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
+  total += 4 * (2 * (size_t)hp.n_embd + qkv + 3 * (size_t)hp.n_embd + (size_t)hp.n_ff + (size_t)hp.n_vocab) + 64 * 256;
+  total += 1 << 20;
+  return total;
+}
+
+void* Engine::alloc(size_t bytes, size_t align) {
+  const size_t off = align_up(arena_used_, align);
+  if (off + bytes > arena_size_) throw std::runtime_error("device arena exhausted");
+  arena_used_ = off + bytes;
+  return arena_ + off;
+}
+
+DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging) {
+  if (!supported_matrix_type(t.type)) throw std::runtime_error("tensor '" + t.name + "': quantization type " + std::to_string(t.type) + " is not supported by the B200 path");
+  DevMat m;
+  m.type = (int)t.type;
+  m.K = (int)t.ne[0];
+  m.M = (int)(t.ne[1] * t.ne[2] * t.ne[3]);
+  m.nb = m.K / type_block_elems(t.type);
+  m.bytes = t.nbytes;
+  uint16_t *qs = nullptr, *qh = nullptr, *sc = nullptr, *d = nullptr;
+  const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, t.nbytes);
+  qs = (uint16_t*)alloc(ps.qs);
+  if (ps.qh) qh = (uint16_t*)alloc(ps.qh);
+  if (ps.sc) sc = (uint16_t*)alloc(ps.sc);
+  if (ps.d) d = (uint16_t*)alloc(ps.d);
+  CTB_CUDA(cudaMemcpyAsync(staging, t.data, t.nbytes, cudaMemcpyHostToDevice, stream_));
+  const size_t n_u16 = t.nbytes / 2;
+  const int grid = (int)std::min<size_t>((n_u16 + 255) / 256, (size_t)sm_count_ * 32);
+  k_repack<<<grid, 256, 0, stream_>>>(m.type, (const uint16_t*)staging, n_u16, qs, qh, sc, d);
+  CTB_CUDA(cudaGetLastError());
+  CTB_CUDA(cudaStreamSynchronize(stream_));   // staging is reused by the next tensor
+  m.qs = (const uint8_t*)qs; m.qh = (const uint8_t*)qh; m.sc = (const uint8_t*)sc; m.d = d;
+  return m;
+}
+
+const float* Engine::upload_vector(const GGUFFile& g, const std::string& name, bool required) {
+  const GGUFTensor* t = g.tensor(name);
+  if (!t) {
+    if (required) throw std::runtime_error("tensor '" + name + "' not found");
+    return nullptr;
+  }
+  if (t->type != T_F32) throw std::runtime_error("tensor '" + name + "' must be f32");
+  float* d = (float*)alloc(t->nbytes);
+  CTB_CUDA(cudaMemcpy(d, t->data, t->nbytes, cudaMemcpyHostToDevice));
+  return d;
+}
+
+// fp16 <-> fp32 on the host through the F16C-equivalent software path (bit-identical to the device's and the reference's)
+static inline float host_h2f(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu, bits;
+  if (exp == 0) {
+    if (!man) bits = sign;
+    else { int e = -1; do { man <<= 1; e++; } while (!(man & 0x400u)); man &= 0x3ffu; bits = sign | ((uint32_t)(127 - 15 - e) << 23) | (man << 13); }
+  } else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
+  else bits = sign | ((exp + 112) << 23) | (man << 13);
+  float f; memcpy(&f, &bits, 4); return f;
+}
+static inline uint16_t host_f2h(float f) {
+  uint32_t x; memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u, ax = x & 0x7fffffffu;
+  if (ax >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (ax > 0x7f800000u ? (0x200u | ((ax >> 13) & 0x3ffu)) : 0));
+  if (ax >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);
+  if (ax < 0x33000001u) return (uint16_t)sign;
+  const int32_t e = (int32_t)(ax >> 23) - 127;
+  const uint32_t m = (ax & 0x7fffffu) | 0x800000u;
+  if (e < -14) {
+    const uint32_t shift = (uint32_t)(13 + (-14 - e));
+    uint32_t r = m >> shift; const uint32_t rem = m & ((1u << shift) - 1), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (r & 1))) r++;
+    return (uint16_t)(sign | r);
+  }
+  uint32_t hb = ((uint32_t)(e + 15) << 10) | ((m >> 13) & 0x3ffu);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (hb & 1))) hb++;
+  return (uint16_t)(sign | hb);
+}
+
+Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), device_(device) {
+  CTB_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  CTB_CUDA(cudaGetDeviceProperties(&prop, device_));
+  sm_count_ = prop.multiProcessorCount;
+  CTB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  CTB_CUDA(cudaEventCreate(&ev0_));
+  CTB_CUDA(cudaEventCreate(&ev1_));
+
+  arena_size_ = engine_arena_bytes(g, hp_);
+  CTB_CUDA(cudaMalloc(&arena_, arena_size_));
+  uint8_t* staging = (uint8_t*)alloc(align_up(max_raw_tensor_bytes(g), 256));
+
+  // ---- weights
+  const std::string pfx = "blk.";
+  {
+    const GGUFTensor& te = g.need_tensor("token_embd.weight");
+    if (!supported_matrix_type(te.type)) throw std::runtime_error("token_embd.weight: unsupported type");
+    uint8_t* d = (uint8_t*)alloc(te.nbytes);
+    CTB_CUDA(cudaMemcpy(d, te.data, te.nbytes, cudaMemcpyHostToDevice));
+    tok_embd_ = d; tok_type_ = (int)te.type;
+    tok_row_bytes_ = te.ne[0] / type_block_elems(te.type) * type_block_bytes(te.type);
+    if ((int)te.ne[0] != hp_.n_embd) throw std::runtime_error("token_embd.weight has wrong shape");
+  }
+  out_norm_ = upload_vector(g, "output_norm.weight", true);
+  out_norm_b_ = upload_vector(g, "output_norm.bias", hp_.falcon);
+  output_ = upload_matrix(g.need_tensor("output.weight"), staging);
+  size_t wbytes = output_.bytes;
+  layers_.resize(hp_.n_layer);
+  for (int il = 0; il < hp_.n_layer; il++) {
+    LayerW& L = layers_[il];
+    const std::string b = pfx + std::to_string(il) + ".";
+    L.attn_norm = upload_vector(g, b + "attn_norm.weight", true);
+    if (hp_.falcon) {
+      L.attn_norm_b = upload_vector(g, b + "attn_norm.bias", true);
+      L.attn_norm2 = upload_vector(g, b + "attn_norm_2.weight", false);
+      if (L.attn_norm2) L.attn_norm2_b = upload_vector(g, b + "attn_norm_2.bias", true);
+      L.wqkv = upload_matrix(g.need_tensor(b + "attn_qkv.weight"), staging);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging);
+      wbytes += L.wqkv.bytes + L.wo.bytes + L.w3.bytes + L.w2.bytes;
+    } else {
+      L.ffn_norm = upload_vector(g, b + "ffn_norm.weight", true);
+      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), staging);
+      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), staging);
+      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), staging);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging);
+      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), staging);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging);
+      wbytes += L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.w1.bytes + L.w2.bytes + L.w3.bytes;
+      if (act_format_for(L.w1.type) != act_format_for(L.w3.type)) throw std::runtime_error("ffn_gate / ffn_up use incompatible quantization families");
+    }
+  }
+  stats.weight_bytes_per_token = wbytes;
+
+  // ---- lookup tables, built with the host libm exactly like ggml_init does (ggml.c:4319-4333)
+  {
+    std::vector<uint16_t> silu(65536), gelu(65536), ex(65536);
+    for (int i = 0; i < 65536; i++) {
+      const float f = host_h2f((uint16_t)i);
+      silu[i] = host_f2h(f / (1.0f + expf(-f)));
+      gelu[i] = host_f2h(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))));
+      ex[i] = host_f2h(expf(f));
+    }
+    silu_tab_ = (uint16_t*)alloc(65536 * 2); gelu_tab_ = (uint16_t*)alloc(65536 * 2); exp_tab_ = (uint16_t*)alloc(65536 * 2);
+    CTB_CUDA(cudaMemcpy(silu_tab_, silu.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    CTB_CUDA(cudaMemcpy(gelu_tab_, gelu.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    CTB_CUDA(cudaMemcpy(exp_tab_, ex.data(), 65536 * 2, cudaMemcpyHostToDevice));
+  }
+  // ---- RoPE table: same recurrence, same libm calls as ggml.c:12482-12529
+  {
+    const int half = hp_.head_dim() / 2;
+    std::vector<float2> tab((size_t)hp_.n_ctx * half);
+    const float theta_scale = powf(hp_.rope_base, -2.0f / hp_.n_rot);
+    for (int p = 0; p < hp_.n_ctx; p++) {
+      float theta = hp_.rope_scale * (float)p;
+      for (int i = 0; i < half; i++) {
+        tab[(size_t)p * half + i] = make_float2(cosf(theta), sinf(theta));
+        theta *= theta_scale;
+      }
+    }
+    rope_ = (float2*)alloc(tab.size() * sizeof(float2));
+    CTB_CUDA(cudaMemcpy(rope_, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  }
+  // ---- KV cache + workspace
+  const size_t kv = (size_t)hp_.n_layer * hp_.n_ctx * hp_.n_embd_gqa();
+  kc_ = (uint16_t*)alloc(kv * 2);
+  vc_ = (uint16_t*)alloc(kv * 2);
+  CTB_CUDA(cudaMemset(kc_, 0, kv * 2));
+  CTB_CUDA(cudaMemset(vc_, 0, kv * 2));
+  const size_t qkv = (size_t)hp_.n_embd + 2 * (size_t)hp_.n_embd_gqa();
+  d_state_ = (int*)alloc(64);
+  xa_ = (float*)alloc(hp_.n_embd * 4); xb_ = (float*)alloc(hp_.n_embd * 4);
+  qkv_ = (float*)alloc(qkv * 4);
+  attn_ = (float*)alloc(hp_.n_embd * 4); attn_o_ = (float*)alloc(hp_.n_embd * 4);
+  ffn_ = (float*)alloc((size_t)hp_.n_ff * 4);
+  d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
+  d_embd_ = (float*)alloc(hp_.n_embd * 4);
+  CTB_CUDA(cudaMemset(d_state_, 0, 64));
+  CTB_CUDA(cudaMallocHost(&h_logits_, (size_t)hp_.n_vocab * 4));
+  CTB_CUDA(cudaMallocHost(&h_embd_, (size_t)hp_.n_embd * 4));
+  memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
+  memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
+
+  CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
+  CTB_CUDA(cudaDeviceSynchronize());
+  build_graphs();
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  cudaDeviceSynchronize();
+  destroy_graphs();
+  if (h_logits_) cudaFreeHost(h_logits_);
+  if (h_embd_) cudaFreeHost(h_embd_);
+  if (h_state_) cudaFreeHost(h_state_);
+  if (h_tokens_out_) cudaFreeHost(h_tokens_out_);
+  if (d_tokens_out_) cudaFree(d_tokens_out_);
+  if (arena_) cudaFree(arena_);
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+  if (stream_ && own_stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::set_stream(cudaStream_t s) {
+  if (own_stream_ && stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+  stream_ = s;
+  own_stream_ = false;
+}
+
+void Engine::launch_matvec(MVParams& p) {
+  p.silu_tab = silu_tab_;
+  p.gelu_tab = gelu_tab_;
+  constexpr int R = 2;
+  long units = 0;
+  if (p.pair_silu) units = (p.seg[0].w.M + R - 1) / R;
+  else for (int s = 0; s < p.nseg; s++) units += (p.seg[s].w.M + R - 1) / R;
+  const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)sm_count_ * 8));
+  const size_t smem = act_smem_bytes(p.act, p.K);
+  if (smem > 48 * 1024) CTB_CUDA(cudaFuncSetAttribute(k_matvec<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_matvec<R><<<grid, MV_THREADS, smem, stream_>>>(p);
+  launches_per_step_++;
+  mark(0);
+}
+
+static MVSeg seg(const DevMat& w, float* out, int epi = EPI_STORE, const float* res = nullptr, const float* res2 = nullptr) {
+  MVSeg s;
+  s.w = w; s.out = out; s.res = res; s.res2 = res2; s.epi = epi;
+  return s;
+}
+
+// One token through the whole model.  Reads {token, n_past} from d_state_.
+void Engine::enqueue_step(bool with_logits, bool greedy) {
+  const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = hp_.n_head_kv, gqa = hp_.n_embd_gqa();
+  const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
+  launches_per_step_ = 0;
+  mark(-1);
+  k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
+  launches_per_step_++;
+  mark(3);
+  float* x = xa_;
+  float* y = xb_;
+  for (int il = 0; il < hp_.n_layer; il++) {
+    const LayerW& L = layers_[il];
+    uint16_t* kc = kc_ + (size_t)il * hp_.n_ctx * gqa;
+    uint16_t* vc = vc_ + (size_t)il * hp_.n_ctx * gqa;
+    RopeKVParams rp{};
+    rp.kc = kc; rp.vc = vc; rp.rope = rope_; rp.n_past = d_state_ + 1;
+    rp.n_head = hp_.n_head; rp.n_kv = n_kv; rp.hd = hd; rp.n_ctx = hp_.n_ctx; rp.neox = hp_.falcon ? 1 : 0;
+    AttnParams ap{};
+    ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.n_past = d_state_ + 1; ap.kq_scale = kq_scale;
+    ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx;
+
+    if (!hp_.falcon) {
+      float* q = qkv_; float* k = qkv_ + n_embd; float* v = qkv_ + n_embd + gqa;
+      {  // attention_norm + wq/wk/wv
+        MVParams p{};
+        p.x = x; p.norm_w = L.attn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+        const DevMat* ws[3] = {&L.wq, &L.wk, &L.wv};
+        float* outs[3] = {q, k, v};
+        bool done[3] = {false, false, false};
+        for (int i = 0; i < 3; i++) {   // group tensors that share an activation format into one launch
+          if (done[i]) continue;
+          p.act = act_format_for(ws[i]->type); p.nseg = 0;
+          for (int j = i; j < 3; j++)
+            if (!done[j] && act_format_for(ws[j]->type) == p.act) { p.seg[p.nseg++] = seg(*ws[j], outs[j]); done[j] = true; }
+          launch_matvec(p);
+        }
+      }
+      rp.q = q; rp.k = k; rp.v = v; rp.q_stride = n_embd; rp.kv_stride = gqa;
+      k_rope_kv<<<dim3(1, hp_.n_head + n_kv), hd / 2, 0, stream_>>>(rp);
+      mark(2);
+      ap.q = q; ap.q_stride = n_embd;
+      k_attn<<<dim3(hp_.n_head, 1), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      mark(1);
+      launches_per_step_ += 2;
+      {  // wo + residual
+        MVParams p{};
+        p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
+        p.seg[0] = seg(L.wo, y, EPI_ADD, x);
+        launch_matvec(p);
+      }
+      {  // ffn_norm + silu(w1 x) * (w3 x)
+        MVParams p{};
+        p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+        p.act = act_format_for(L.w1.type); p.nseg = 2; p.pair_silu = 1;
+        p.seg[0] = seg(L.w1, ffn_); p.seg[1] = seg(L.w3, nullptr);
+        launch_matvec(p);
+      }
+      {  // w2 + residual
+        MVParams p{};
+        p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.seg[0] = seg(L.w2, x, EPI_ADD, y);
+        launch_matvec(p);
+      }
+      // x now holds the next layer's input
+    } else {
+      const int qkv_w = (hp_.n_head + 2 * n_kv) * hd;
+      float* q = qkv_; float* k = qkv_ + (size_t)hp_.n_head * hd; float* v = k + (size_t)n_kv * hd;
+      const bool two_norms = L.attn_norm2 != nullptr;
+      const bool fuse = !two_norms && act_format_for(L.wqkv.type) == act_format_for(L.w3.type);
+      {  // LayerNorm + wqkv (+ ffn_up → GELU when it shares the normed input)
+        MVParams p{};
+        p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd;
+        p.norm_w = two_norms ? L.attn_norm2 : L.attn_norm; p.norm_b = two_norms ? L.attn_norm2_b : L.attn_norm_b;
+        p.act = act_format_for(L.wqkv.type); p.nseg = 1;
+        p.seg[0] = seg(L.wqkv, qkv_);
+        if (fuse) { p.seg[1] = seg(L.w3, ffn_, EPI_GELU); p.nseg = 2; }
+        launch_matvec(p);
+      }
+      if (!fuse) {
+        MVParams p{};
+        p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd; p.norm_w = L.attn_norm; p.norm_b = L.attn_norm_b;
+        p.act = act_format_for(L.w3.type); p.nseg = 1;
+        p.seg[0] = seg(L.w3, ffn_, EPI_GELU);
+        launch_matvec(p);
+      }
+      rp.q = q; rp.k = k; rp.v = v; rp.q_stride = qkv_w; rp.kv_stride = qkv_w;
+      k_rope_kv<<<dim3(1, hp_.n_head + n_kv), hd / 2, 0, stream_>>>(rp);
+      mark(2);
+      ap.q = q; ap.q_stride = qkv_w;
+      k_attn<<<dim3(hp_.n_head, 1), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      mark(1);
+      launches_per_step_ += 2;
+      {  // attention output projection
+        MVParams p{};
+        p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
+        p.seg[0] = seg(L.wo, attn_o_);
+        launch_matvec(p);
+      }
+      {  // ffn_down, then + attn_out, then + layer input (llama.cpp:2767-2771 order)
+        MVParams p{};
+        p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.seg[0] = seg(L.w2, y, EPI_ADD2, attn_o_, x);
+        launch_matvec(p);
+      }
+      std::swap(x, y);
+    }
+  }
+  if (with_logits) {
+    MVParams p{};
+    p.x = x; p.norm_w = out_norm_; p.norm_b = out_norm_b_; p.norm_mode = hp_.falcon ? NORM_LAYER : NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+    p.norm_out = d_embd_; p.act = act_format_for(output_.type); p.nseg = 1;
+    p.seg[0] = seg(output_, d_logits_);
+    launch_matvec(p);
+    if (greedy) {
+      k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 3);
+      k_advance<<<1, 1, 0, stream_>>>(d_state_ + 3, d_state_, d_tokens_out_);
+      launches_per_step_ += 2;
+    }
+  }
+  CTB_CUDA(cudaGetLastError());
+}
+
+void Engine::mark(int kind) {
+  if (!profiling_) return;
+  cudaEvent_t e;
+  CTB_CUDA(cudaEventCreate(&e));
+  CTB_CUDA(cudaEventRecord(e, stream_));
+  prof_ev_.push_back(e);
+  prof_kind_.push_back(kind);
+}
+
+int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
+  CTB_CUDA(cudaSetDevice(device_));
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
+  h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = 0;
+  CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
+  const long keep = launches_per_step_;
+  profiling_ = true;
+  try { enqueue_step(true, false); } catch (...) { profiling_ = false; throw; }
+  profiling_ = false;
+  launches_per_step_ = keep;
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  int n = 0;
+  for (size_t i = 1; i < prof_ev_.size(); i++) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, prof_ev_[i - 1], prof_ev_[i]);
+    const int k = prof_kind_[i];
+    if (k >= 0 && k < 4) { ms_by_kind[k] += ms; count_by_kind[k]++; n++; }
+  }
+  for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
+  prof_ev_.clear(); prof_kind_.clear();
+  return n;
+}
+
+void Engine::destroy_graphs() {
+  if (graph_full_) cudaGraphExecDestroy(graph_full_);
+  if (graph_nolog_) cudaGraphExecDestroy(graph_nolog_);
+  if (graph_greedy_) cudaGraphExecDestroy(graph_greedy_);
+  graph_full_ = graph_nolog_ = graph_greedy_ = nullptr;
+}
+
+void Engine::build_graphs() {
+  destroy_graphs();
+  if (!d_tokens_out_) {
+    tokens_out_cap_ = std::max(hp_.n_ctx, 4096);
+    CTB_CUDA(cudaMalloc(&d_tokens_out_, (size_t)tokens_out_cap_ * 4));
+    CTB_CUDA(cudaMallocHost(&h_tokens_out_, (size_t)tokens_out_cap_ * 4));
+  }
+  cudaStream_t user = stream_;
+  cudaStream_t cap;
+  CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  stream_ = cap;
+  auto capture = [&](bool logits, bool greedy) {
+    cudaGraph_t g;
+    CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    enqueue_step(logits, greedy);
+    CTB_CUDA(cudaStreamEndCapture(cap, &g));
+    cudaGraphExec_t ex;
+    CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+    return ex;
+  };
+  try {
+    graph_nolog_ = capture(false, false);
+    graph_greedy_ = capture(true, true);
+    graph_full_ = capture(true, false);
+  } catch (...) {
+    stream_ = user;
+    cudaStreamDestroy(cap);
+    throw;
+  }
+  stats.launches = launches_per_step_;
+  stream_ = user;
+  cudaStreamDestroy(cap);
+}
+
+void Engine::eval(const int* tokens, int n, int n_past) {
+  if (n <= 0) return;
+  CTB_CUDA(cudaSetDevice(device_));
+  if (h_state_cap_ < n) {
+    if (h_state_) cudaFreeHost(h_state_);
+    h_state_cap_ = std::max(n, 512);
+    CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16));
+  }
+  CTB_CUDA(cudaEventRecord(ev0_, stream_));
+  for (int i = 0; i < n; i++) {
+    int* st = h_state_ + (size_t)i * 4;
+    st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = 0;
+    CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
+    CTB_CUDA(cudaGraphLaunch(i == n - 1 ? graph_full_ : graph_nolog_, stream_));
+  }
+  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaEventRecord(ev1_, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0_, ev1_);
+  stats.last_eval_ms = ms;
+}
+
+double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens) {
+  if (n_steps <= 0) return 0.0;
+  if (n_steps > tokens_out_cap_) throw std::runtime_error("decode_greedy: too many steps");
+  if (n_past + n_steps > hp_.n_ctx) throw std::runtime_error("decode_greedy: would run past the context length");
+  CTB_CUDA(cudaSetDevice(device_));
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
+  h_state_[0] = first_token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = 0;
+  CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
+  CTB_CUDA(cudaEventRecord(ev0_, stream_));
+  for (int s = 0; s < n_steps; s++) CTB_CUDA(cudaGraphLaunch(graph_greedy_, stream_));
+  CTB_CUDA(cudaEventRecord(ev1_, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_tokens_out_, d_tokens_out_, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  memcpy(out_tokens, h_tokens_out_, (size_t)n_steps * 4);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0_, ev1_);
+  stats.last_eval_ms = ms;
+  return ms;
+}
+
+}  // namespace ctb

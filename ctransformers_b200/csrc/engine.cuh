@@ -1,0 +1,110 @@
+// Eval engine: static device arena + fixed op schedule for the two graph shapes of the path
+// (llm_build_llama / llm_build_falcon, reference models/ggml/llama.cpp:2162-2798) driven like
+// llama_eval_internal (llama.cpp:2835-2981): last token's logits and post-final-norm hidden state end
+// up in host memory owned by the LLM object.
+//
+// B200 design: weights repacked once into coalesced planes (device_types.cuh); KV cache fp16;
+// one CUDA graph per decode step shape with {token, n_past} as device scalars, so the same graph
+// replays for every position; no per-eval graph build, no allocator, no thread pool.
+#pragma once
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "device_types.cuh"
+#include "gguf.hpp"
+
+namespace ctb {
+
+struct HParams {
+  bool falcon = false;
+  int n_vocab = 0, n_ctx_train = 0, n_embd = 0, n_ff = 0, n_head = 0, n_head_kv = 0, n_layer = 0, n_rot = 0;
+  float eps = 1e-5f, rope_base = 10000.f, rope_scale = 1.f;
+  int n_ctx = 512;
+  int head_dim() const { return n_embd / n_head; }
+  int n_embd_gqa() const { return head_dim() * n_head_kv; }
+};
+
+struct LayerW {
+  DevMat wq, wk, wv, wqkv, wo, w1, w2, w3;
+  const float* attn_norm = nullptr; const float* attn_norm_b = nullptr;
+  const float* attn_norm2 = nullptr; const float* attn_norm2_b = nullptr;
+  const float* ffn_norm = nullptr;
+};
+
+struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; };
+
+class Engine {
+ public:
+  Engine(const GGUFFile& g, const HParams& hp, int device);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  // Evaluate n tokens starting at position n_past; afterwards logits()/embeddings() hold the last token's.
+  void eval(const int* tokens, int n, int n_past);
+  // n_steps greedy decode steps entirely on the device stream (token feedback through k_argmax);
+  // out_tokens[n_steps] receives the picked ids.  Returns device-timed milliseconds for the steps.
+  double decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens);
+  // One eager (un-graphed) decode step at n_past with a CUDA event after every kernel; accumulates the
+  // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
+  int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
+
+  float* logits() { return h_logits_; }
+  float* embeddings() { return h_embd_; }
+  const HParams& hparams() const { return hp_; }
+  EvalStats stats;
+  void set_stream(cudaStream_t s);   // run on a caller-owned stream (bench: torch's current stream)
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  HParams hp_;
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  bool own_stream_ = true;
+  // arena
+  uint8_t* arena_ = nullptr;
+  size_t arena_size_ = 0, arena_used_ = 0;
+  void* alloc(size_t bytes, size_t align = 256);
+
+  // weights
+  DevMat output_;
+  const uint8_t* tok_embd_ = nullptr; int tok_type_ = 0; size_t tok_row_bytes_ = 0;
+  const float* out_norm_ = nullptr; const float* out_norm_b_ = nullptr;
+  std::vector<LayerW> layers_;
+  uint16_t *silu_tab_ = nullptr, *gelu_tab_ = nullptr, *exp_tab_ = nullptr;
+  float2* rope_ = nullptr;
+  // KV cache
+  uint16_t *kc_ = nullptr, *vc_ = nullptr;
+  // workspace
+  int* d_state_ = nullptr;     // {token, n_past}
+  float *xa_ = nullptr, *xb_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *attn_o_ = nullptr, *ffn_ = nullptr, *d_logits_ = nullptr, *d_embd_ = nullptr;
+  // host (pinned) results
+  float *h_logits_ = nullptr, *h_embd_ = nullptr;
+  int* h_state_ = nullptr;     // pinned ring of {token, n_past}
+  int h_state_cap_ = 0;
+  int* h_tokens_out_ = nullptr;
+  int* d_tokens_out_ = nullptr;
+  int tokens_out_cap_ = 0;
+
+  cudaGraphExec_t graph_full_ = nullptr, graph_nolog_ = nullptr, graph_greedy_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  int sm_count_ = 148;
+  long launches_per_step_ = 0;
+
+  DevMat upload_matrix(const GGUFTensor& t, uint8_t* staging);
+  const float* upload_vector(const GGUFFile& g, const std::string& name, bool required);
+  void enqueue_step(bool with_logits, bool greedy);
+  void build_graphs();
+  void destroy_graphs();
+  void launch_matvec(struct MVParams& p);
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> prof_ev_;
+  std::vector<int> prof_kind_;
+  void mark(int kind);
+};
+
+size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp);
+
+}  // namespace ctb

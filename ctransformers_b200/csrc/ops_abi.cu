@@ -1,0 +1,277 @@
+// Op-level C entry points (include/ctransformers_b200.h, part 2): each mirrors one ggml operator of the hot
+// path with plain host pointers, runs the SAME device code the engine runs (matvec.cuh / attention.cuh), and
+// copies the result back.  Used by the parity tests and usable by a maintainer who wants to swap one op.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ctransformers_b200.h"
+#include "attention.cuh"
+#include "matvec.cuh"
+#include "repack.cuh"
+
+using namespace ctb;
+
+namespace {
+
+#define OPS_CUDA(expr)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t e__ = (expr);                                                                              \
+    if (e__ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " (" #expr ")"); \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  explicit DevBuf(size_t n) { OPS_CUDA(cudaMalloc(&p, n ? n : 1)); }
+  ~DevBuf() { if (p) cudaFree(p); }
+  DevBuf(const DevBuf&) = delete;
+  template <typename T> T* as() const { return (T*)p; }
+};
+
+struct OpsTables {
+  uint16_t *silu = nullptr, *gelu = nullptr, *ex = nullptr;
+};
+
+// built once per process, on the host with libm, like ggml_init (ggml.c:4319-4333)
+OpsTables& tables() {
+  static OpsTables t;
+  if (!t.silu) {
+    std::vector<uint16_t> s(65536), g(65536), e(65536);
+    for (int i = 0; i < 65536; i++) {
+      const float f = __half2float(__ushort_as_half((uint16_t)i));
+      s[i] = __half_as_ushort(__float2half_rn(f / (1.0f + expf(-f))));
+      g[i] = __half_as_ushort(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)))));
+      e[i] = __half_as_ushort(__float2half_rn(expf(f)));
+    }
+    OPS_CUDA(cudaMalloc(&t.silu, 65536 * 2)); OPS_CUDA(cudaMalloc(&t.gelu, 65536 * 2)); OPS_CUDA(cudaMalloc(&t.ex, 65536 * 2));
+    OPS_CUDA(cudaMemcpy(t.silu, s.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(t.gelu, g.data(), 65536 * 2, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(t.ex, e.data(), 65536 * 2, cudaMemcpyHostToDevice));
+  }
+  return t;
+}
+
+size_t raw_row_bytes(int type, int K) {
+  switch (type) {
+    case GT_F32: return (size_t)K * 4; case GT_F16: return (size_t)K * 2;
+    case GT_Q4_0: return (size_t)K / 32 * 18; case GT_Q8_0: return (size_t)K / 32 * 34;
+    case GT_Q4_K: return (size_t)K / 256 * 144; case GT_Q5_K: return (size_t)K / 256 * 176; case GT_Q6_K: return (size_t)K / 256 * 210;
+  }
+  throw std::runtime_error("unsupported ggml type " + std::to_string(type));
+}
+int block_elems(int type) { return type_is_kquant(type) ? 256 : (type == GT_Q4_0 || type == GT_Q8_0) ? 32 : 1; }
+
+struct OwnedMat {
+  DevMat m;
+  std::vector<void*> bufs;
+  ~OwnedMat() { for (void* b : bufs) cudaFree(b); }
+};
+
+void upload(OwnedMat& o, int type, const void* blocks, int K, int M) {
+  if (K % block_elems(type)) throw std::runtime_error("K is not a multiple of the block size");
+  const size_t bytes = raw_row_bytes(type, K) * M;
+  DevBuf raw(bytes);
+  OPS_CUDA(cudaMemcpy(raw.p, blocks, bytes, cudaMemcpyHostToDevice));
+  o.m.type = type; o.m.K = K; o.m.M = M; o.m.nb = K / block_elems(type); o.m.bytes = bytes;
+  const PlaneSizes ps = plane_sizes(type, M, o.m.nb, bytes);
+  uint16_t* pl[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t sz[4] = {ps.qs, ps.qh, ps.sc, ps.d};
+  for (int i = 0; i < 4; i++)
+    if (sz[i]) { OPS_CUDA(cudaMalloc((void**)&pl[i], sz[i])); o.bufs.push_back(pl[i]); }
+  k_repack<<<(int)std::min<size_t>((bytes / 2 + 255) / 256, 4096), 256>>>(type, raw.as<uint16_t>(), bytes / 2, pl[0], pl[1], pl[2], pl[3]);
+  OPS_CUDA(cudaDeviceSynchronize());
+  o.m.qs = (const uint8_t*)pl[0]; o.m.qh = (const uint8_t*)pl[1]; o.m.sc = (const uint8_t*)pl[2]; o.m.d = pl[3];
+}
+
+void run_matvec(MVParams& p) {
+  constexpr int R = 2;
+  p.silu_tab = tables().silu;
+  p.gelu_tab = tables().gelu;
+  long units = 0;
+  if (p.pair_silu) units = (p.seg[0].w.M + R - 1) / R;
+  else for (int s = 0; s < p.nseg; s++) units += (p.seg[s].w.M + R - 1) / R;
+  const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, 148L * 8));
+  const size_t smem = act_smem_bytes(p.act, p.K);
+  if (smem > 48 * 1024) OPS_CUDA(cudaFuncSetAttribute(k_matvec<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_matvec<R><<<grid, MV_THREADS, smem>>>(p);
+  OPS_CUDA(cudaGetLastError());
+}
+
+// standalone wrappers around the prologue pieces, so the activation quantizers can be checked bit-for-bit
+__global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const float* nw, const float* nb, float* norm_out, int mode, float eps, int K, int act,
+                                                            uint8_t* dump) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ double red[MV_WARPS];
+  stage_activation(x, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
+  const size_t n = act_smem_bytes(act, K);
+  for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
+}
+
+int guarded(const char* what, const std::function<void()>& fn) {
+  try {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) throw std::runtime_error("no CUDA device available (no CPU fallback)");
+    fn();
+    return 0;
+  } catch (const std::exception& e) {
+    fprintf(stderr, "ctransformers-b200: %s failed: %s\n", what, e.what());
+    return -1;
+  }
+}
+
+void stage_to_host(const float* x, const float* w, const float* b, float* y_norm, int mode, float eps, int K, int act, std::vector<uint8_t>& dump) {
+  DevBuf dx((size_t)K * 4), dw((size_t)K * 4), db((size_t)K * 4), dy((size_t)K * 4);
+  OPS_CUDA(cudaMemcpy(dx.p, x, (size_t)K * 4, cudaMemcpyHostToDevice));
+  if (w) OPS_CUDA(cudaMemcpy(dw.p, w, (size_t)K * 4, cudaMemcpyHostToDevice));
+  if (b) OPS_CUDA(cudaMemcpy(db.p, b, (size_t)K * 4, cudaMemcpyHostToDevice));
+  const size_t n = act_smem_bytes(act, K);
+  DevBuf dd(n);
+  if (n > 48 * 1024) OPS_CUDA(cudaFuncSetAttribute(k_stage_dump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)n));
+  k_stage_dump<<<1, MV_THREADS, n>>>(dx.as<float>(), w ? dw.as<float>() : nullptr, b ? db.as<float>() : nullptr, dy.as<float>(), mode, eps, K, act, dd.as<uint8_t>());
+  OPS_CUDA(cudaGetLastError());
+  dump.resize(n);
+  OPS_CUDA(cudaMemcpy(dump.data(), dd.p, n, cudaMemcpyDeviceToHost));
+  if (y_norm) OPS_CUDA(cudaMemcpy(y_norm, dy.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctb_mul_mat(int type, const void* w_blocks, const float* x, float* dst, int K, int M, int N) {
+  return guarded("ctb_mul_mat", [&] {
+    OwnedMat w;
+    upload(w, type, w_blocks, K, M);
+    DevBuf dx((size_t)K * N * 4), dy((size_t)M * N * 4);
+    OPS_CUDA(cudaMemcpy(dx.p, x, (size_t)K * N * 4, cudaMemcpyHostToDevice));
+    for (int n = 0; n < N; n++) {
+      MVParams p{};
+      p.x = dx.as<float>() + (size_t)n * K; p.norm_mode = NORM_NONE; p.K = K; p.act = act_format_for(type); p.nseg = 1;
+      p.seg[0].w = w.m; p.seg[0].out = dy.as<float>() + (size_t)n * M; p.seg[0].epi = EPI_STORE;
+      run_matvec(p);
+    }
+    OPS_CUDA(cudaMemcpy(dst, dy.p, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int ctb_quantize_row_q8_K(const float* x, void* y, int k) {
+  return guarded("ctb_quantize_row_q8_K", [&] {
+    if (k % 256) throw std::runtime_error("k must be a multiple of 256");
+    std::vector<uint8_t> dump;
+    stage_to_host(x, nullptr, nullptr, nullptr, NORM_NONE, 0.f, k, ACT_Q8_K, dump);
+    const int nb = k / 256;
+    const size_t off = ((size_t)k + 15) & ~(size_t)15;
+    const float* d = (const float*)(dump.data() + off);
+    const int16_t* bs = (const int16_t*)(dump.data() + off + (size_t)nb * 4);
+    uint8_t* out = (uint8_t*)y;   // block_q8_K: float d; int8 qs[256]; int16 bsums[16]  (k_quants.h:121-125)
+    for (int b = 0; b < nb; b++) {
+      memcpy(out + (size_t)b * 292, d + b, 4);
+      memcpy(out + (size_t)b * 292 + 4, dump.data() + (size_t)b * 256, 256);
+      memcpy(out + (size_t)b * 292 + 260, bs + (size_t)b * 16, 32);
+    }
+  });
+}
+
+int ctb_quantize_row_q8_0(const float* x, void* y, int k) {
+  return guarded("ctb_quantize_row_q8_0", [&] {
+    if (k % 32) throw std::runtime_error("k must be a multiple of 32");
+    std::vector<uint8_t> dump;
+    stage_to_host(x, nullptr, nullptr, nullptr, NORM_NONE, 0.f, k, ACT_Q8_0, dump);
+    const int nb = k / 32;
+    const size_t off = ((size_t)k + 15) & ~(size_t)15;
+    const float* d = (const float*)(dump.data() + off);
+    uint8_t* out = (uint8_t*)y;   // block_q8_0: fp16 d; int8 qs[32]  (ggml.c:920-925)
+    for (int b = 0; b < nb; b++) {
+      const uint16_t h = __half_as_ushort(__float2half_rn(d[b]));   // d[b] is already fp16-representable
+      memcpy(out + (size_t)b * 34, &h, 2);
+      memcpy(out + (size_t)b * 34 + 2, dump.data() + (size_t)b * 32, 32);
+    }
+  });
+}
+
+int ctb_norm(int mode, const float* x, const float* w, const float* b, float* y, int n, float eps) {
+  return guarded("ctb_norm", [&] {
+    std::vector<uint8_t> dump;
+    stage_to_host(x, w, b, y, mode, eps, n, ACT_F32, dump);
+  });
+}
+
+int ctb_rope(float* x, int n_heads, int head_dim, int pos, int mode, float freq_base, float freq_scale) {
+  return guarded("ctb_rope", [&] {
+    const int half = head_dim / 2;
+    std::vector<float2> tab((size_t)(pos + 1) * half);
+    const float theta_scale = powf(freq_base, -2.0f / head_dim);
+    for (int p = 0; p <= pos; p++) {
+      float theta = freq_scale * (float)p;
+      for (int i = 0; i < half; i++) { tab[(size_t)p * half + i] = make_float2(cosf(theta), sinf(theta)); theta *= theta_scale; }
+    }
+    const size_t nq = (size_t)n_heads * head_dim;
+    DevBuf dq(nq * 4), dk(nq * 4), dtab(tab.size() * 8), dkc((size_t)(pos + 1) * head_dim * 2), dvc((size_t)(pos + 1) * head_dim * 2), dn(4);
+    OPS_CUDA(cudaMemcpy(dq.p, x, nq * 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dk.p, x, nq * 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dtab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dn.p, &pos, 4, cudaMemcpyHostToDevice));
+    RopeKVParams rp{};
+    rp.q = dq.as<float>(); rp.k = dk.as<float>(); rp.v = dk.as<float>(); rp.kc = dkc.as<uint16_t>(); rp.vc = dvc.as<uint16_t>();
+    rp.rope = dtab.as<float2>(); rp.n_past = dn.as<int>(); rp.n_head = n_heads; rp.n_kv = 1; rp.hd = head_dim; rp.n_ctx = pos + 1;
+    rp.neox = (mode & 2) ? 1 : 0; rp.q_stride = (int)nq; rp.kv_stride = (int)nq;
+    k_rope_kv<<<dim3(1, n_heads), half>>>(rp);   // only the Q heads (grid.y == n_head ⇒ no KV block)
+    OPS_CUDA(cudaGetLastError());
+    OPS_CUDA(cudaMemcpy(x, dq.p, nq * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache, float* out, int n_head, int n_kv, int head_dim, int T,
+                  float kq_scale) {
+  return guarded("ctb_attention", [&] {
+    if (head_dim != 64 && head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");
+    const size_t nq = (size_t)n_head * head_dim, nkv = (size_t)T * n_kv * head_dim;
+    DevBuf dq(nq * 4), dk(nkv * 2), dv(nkv * 2), dout(nq * 4), dn(4);
+    OPS_CUDA(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dk.p, kcache, nkv * 2, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dv.p, vcache, nkv * 2, cudaMemcpyHostToDevice));
+    const int n_past = T - 1;
+    OPS_CUDA(cudaMemcpy(dn.p, &n_past, 4, cudaMemcpyHostToDevice));
+    AttnParams ap{};
+    ap.q = dq.as<float>(); ap.kc = dk.as<uint16_t>(); ap.vc = dv.as<uint16_t>(); ap.out = dout.as<float>(); ap.exp_tab = tables().ex;
+    ap.n_past = dn.as<int>(); ap.kq_scale = kq_scale; ap.n_head = n_head; ap.n_kv = n_kv; ap.hd = head_dim; ap.n_ctx = T; ap.q_stride = (int)nq;
+    const size_t smem = attn_smem_bytes(T, head_dim);
+    OPS_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    k_attn<<<dim3(n_head, 1), ATTN_THREADS, smem>>>(ap);
+    OPS_CUDA(cudaGetLastError());
+    OPS_CUDA(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const float* x, float* out, int K, int M) {
+  return guarded("ctb_ffn_gate", [&] {
+    OwnedMat w1, w3;
+    upload(w1, type, w1_blocks, K, M);
+    upload(w3, type, w3_blocks, K, M);
+    DevBuf dx((size_t)K * 4), dy((size_t)M * 4);
+    OPS_CUDA(cudaMemcpy(dx.p, x, (size_t)K * 4, cudaMemcpyHostToDevice));
+    MVParams p{};
+    p.x = dx.as<float>(); p.norm_mode = NORM_NONE; p.K = K; p.act = act_format_for(type); p.nseg = 2; p.pair_silu = 1;
+    p.seg[0].w = w1.m; p.seg[0].out = dy.as<float>(); p.seg[1].w = w3.m;
+    run_matvec(p);
+    OPS_CUDA(cudaMemcpy(out, dy.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+int ctb_get_row(int type, const void* table_blocks, int K, int n_rows, int row, float* out) {
+  return guarded("ctb_get_row", [&] {
+    const size_t rb = raw_row_bytes(type, K);
+    DevBuf dt(rb * n_rows), dtok(4), dout((size_t)K * 4);
+    OPS_CUDA(cudaMemcpy(dt.p, table_blocks, rb * n_rows, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dtok.p, &row, 4, cudaMemcpyHostToDevice));
+    k_embed<<<1, 256>>>(dt.as<uint8_t>(), type, rb, K, n_rows, dtok.as<int>(), dout.as<float>());
+    OPS_CUDA(cudaGetLastError());
+    OPS_CUDA(cudaMemcpy(out, dout.p, (size_t)K * 4, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"
