@@ -124,7 +124,7 @@ struct AttnParams {
 constexpr int ATTN_THREADS = 256;
 constexpr int ATTN_WARPS = ATTN_THREADS / 32;
 
-// grid = (n_head, N); dynamic smem = hd*2 + n_ctx*(4+2) + ATTN_WARPS*hd*4
+// grid = (n_head, N); dynamic smem = attn_smem_bytes(n_ctx, hd)
 static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red_f[ATTN_WARPS];
@@ -135,10 +135,11 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   const int kvh = h / (p.n_head / p.n_kv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  float* sc = (float*)smem;                                  // [n_ctx]
-  uint16_t* p16 = (uint16_t*)(smem + (size_t)p.n_ctx * 4);   // [n_ctx]
-  uint16_t* q16 = p16 + p.n_ctx;                             // [hd]
-  float* part = (float*)(smem + (((size_t)p.n_ctx * 6 + (size_t)hd * 2 + 15) & ~(size_t)15));   // [ATTN_WARPS][hd]
+  const size_t ctx_pad = ((size_t)p.n_ctx + 7) & ~(size_t)7;   // keeps every sub-array 16-byte aligned for any n_ctx
+  float* sc = (float*)smem;                                  // [ctx_pad]
+  uint16_t* p16 = (uint16_t*)(smem + ctx_pad * 4);           // [ctx_pad]
+  uint16_t* q16 = p16 + ctx_pad;                             // [hd]
+  float* part = (float*)(smem + ctx_pad * 6 + (size_t)hd * 2);   // [ATTN_WARPS][hd]
 
   const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
   for (int i = threadIdx.x; i < hd; i += ATTN_THREADS) q16[i] = f2h(qv[i]);
@@ -217,7 +218,7 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
 }
 
 __host__ inline size_t attn_smem_bytes(int n_ctx, int hd) {
-  return (((size_t)n_ctx * 6 + (size_t)hd * 2 + 15) & ~(size_t)15) + (size_t)ATTN_WARPS * hd * 4;
+  return (((size_t)n_ctx + 7) & ~(size_t)7) * 6 + (size_t)hd * 2 + (size_t)ATTN_WARPS * hd * 4;
 }
 
 // ----------------------------------------------------------------------------------------- argmax

@@ -124,3 +124,129 @@ def ref_vec_dot(t, k, wrow, act):
     s = np.zeros(1, dtype=np.float32)
     ref_traits(t)["vec_dot"](k, ptr(s), ptr(wrow), ptr(act))
     return float(s[0])
+
+
+# --------------------------------------------------------------------------------------------------------------
+# Whole-model oracle (oracle/llama_oracle.c) driven from a GGUF file
+def read_gguf(path):
+    """Tiny GGUF v2/v3 reader: returns (kv dict, {name: (type, shape, np.uint8 view of the data)})."""
+    import struct
+    buf = np.memmap(path, dtype=np.uint8, mode="r")
+    pos = [0]
+
+    def rd(fmt):
+        v = struct.unpack_from("<" + fmt, buf, pos[0])
+        pos[0] += struct.calcsize("<" + fmt)
+        return v[0] if len(v) == 1 else v
+
+    def rstr():
+        n = rd("Q")
+        s = bytes(buf[pos[0]:pos[0] + n])
+        pos[0] += n
+        return s
+
+    scalar = {0: "B", 1: "b", 2: "H", 3: "h", 4: "I", 5: "i", 6: "f", 7: "?", 10: "Q", 11: "q", 12: "d"}
+    magic, version, n_tensors, n_kv = rd("I"), rd("I"), rd("Q"), rd("Q")
+    assert magic == 0x46554747 and version >= 2
+    kv = {}
+    for _ in range(n_kv):
+        key = rstr().decode()
+        t = rd("I")
+        if t == 8:
+            kv[key] = rstr()
+        elif t == 9:
+            et, n = rd("I"), rd("Q")
+            if et == 8:
+                kv[key] = [rstr() for _ in range(n)]
+            else:
+                sz = struct.calcsize(scalar[et])
+                kv[key] = np.frombuffer(buf, dtype=np.dtype("<" + scalar[et]), count=n, offset=pos[0]).copy()
+                pos[0] += sz * n
+        else:
+            kv[key] = rd(scalar[t])
+    infos = []
+    for _ in range(n_tensors):
+        name = rstr().decode()
+        nd = rd("I")
+        shape = [rd("Q") for _ in range(nd)]
+        t, off = rd("I"), rd("Q")
+        infos.append((name, t, shape, off))
+    align = kv.get("general.alignment", 32)
+    start = (pos[0] + align - 1) // align * align
+    tensors = {}
+    for name, t, shape, off in infos:
+        rows = int(np.prod(shape[1:])) if len(shape) > 1 else 1
+        nbytes = row_bytes(t, shape[0]) * rows
+        tensors[name] = (t, shape, buf[start + off:start + off + nbytes])
+    return kv, tensors
+
+
+class OracleModel:
+    """oracle/llama_oracle.c bound to one GGUF file (keeps the arrays alive)."""
+
+    def __init__(self, path, n_ctx):
+        o = oracle()
+        kv, tensors = read_gguf(path)
+        arch = kv["general.architecture"].decode()
+        g = lambda k, d=None: kv.get(f"{arch}.{k}", d)
+        self.falcon = arch == "falcon"
+        self.n_vocab = len(kv["tokenizer.ggml.tokens"])
+        self.n_embd, self.n_ff, self.n_head, self.n_layer = g("embedding_length"), g("feed_forward_length"), g("attention.head_count"), g("block_count")
+        self.n_head_kv = g("attention.head_count_kv", self.n_head)
+        eps = g("attention.layer_norm_epsilon") if self.falcon else g("attention.layer_norm_rms_epsilon")
+        rope_base = g("rope.freq_base", 10000.0)
+        lin = g("rope.scale_linear", 1.0)
+        o.orc_model_new.restype = C.c_void_p
+        o.orc_model_new.argtypes = [C.c_int] * 8 + [C.c_float] * 3
+        o.orc_model_set_mat.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        o.orc_model_set_vec.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        o.orc_model_set_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        o.orc_model_free.argtypes = [C.c_void_p]
+        o.orc_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self.o, self.keep = o, []
+        self.m = o.orc_model_new(int(self.falcon), self.n_vocab, self.n_embd, self.n_ff, self.n_head, self.n_head_kv, self.n_layer, n_ctx,
+                                 eps, rope_base, 1.0 / lin if lin != 1.0 else 1.0)
+
+        def mat(layer, slot, name):
+            t, shape, data = tensors[name]
+            a = np.ascontiguousarray(data)
+            self.keep.append(a)
+            o.orc_model_set_mat(self.m, layer, slot, t, shape[0], int(np.prod(shape[1:])), ptr(a))
+
+        def vec(layer, slot, name):
+            if name not in tensors:
+                return
+            a = np.ascontiguousarray(tensors[name][2]).view(np.float32)
+            self.keep.append(a)
+            o.orc_model_set_vec(self.m, layer, slot, ptr(a))
+
+        mat(-1, 0, "token_embd.weight")
+        mat(-1, 1, "output.weight")
+        vec(-1, 0, "output_norm.weight")
+        vec(-1, 1, "output_norm.bias")
+        for il in range(self.n_layer):
+            b = f"blk.{il}."
+            vec(il, 0, b + "attn_norm.weight"); vec(il, 1, b + "attn_norm.bias")
+            vec(il, 2, b + "attn_norm_2.weight"); vec(il, 3, b + "attn_norm_2.bias"); vec(il, 4, b + "ffn_norm.weight")
+            names = ({3: "attn_qkv", 4: "attn_output", 6: "ffn_down", 7: "ffn_up"} if self.falcon else
+                     {0: "attn_q", 1: "attn_k", 2: "attn_v", 4: "attn_output", 5: "ffn_gate", 6: "ffn_down", 7: "ffn_up"})
+            for slot, nm in names.items():
+                mat(il, slot, b + nm + ".weight")
+        self.logits = np.zeros(self.n_vocab, np.float32)
+        self.embd = np.zeros(self.n_embd, np.float32)
+        self.trace_layers = np.zeros((self.n_layer, self.n_embd), np.float32)
+        self.trace_attn = np.zeros((self.n_layer, self.n_embd), np.float32)
+        o.orc_model_set_trace(self.m, ptr(self.trace_layers), ptr(self.trace_attn))
+        self.n_past = 0
+
+    def eval(self, tokens):
+        t = np.asarray(tokens, dtype=np.int32)
+        rc = self.o.orc_eval(self.m, ptr(t), len(t), self.n_past, ptr(self.logits), ptr(self.embd))
+        assert rc == 0, rc
+        self.n_past += len(t)
+        return self.logits
+
+    def __del__(self):
+        if getattr(self, "m", None):
+            self.o.orc_model_free(self.m)
+            self.m = None
