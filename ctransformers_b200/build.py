@@ -20,7 +20,7 @@ OBJ_DIR = PKG.parent / "build" / "obj"
 SOURCES = ["engine.cu", "llm_abi.cu", "ops_abi.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-ffp-contract=off", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
 
 

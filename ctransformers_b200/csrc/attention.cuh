@@ -1,8 +1,9 @@
 // Non-matmul stages of the eval graph, each reproducing the reference's rounding points:
 //   k_embed     ggml_get_rows on a quantized token_embd            ggml.c:11615-11642 + dequantize_row_* (k_quants.c:784-821, 984-1026, 1123-1166; ggml.c:1483-1608)
 //   k_rope_kv   RoPE (mode 0 / neox) in place on Q, on K → fp16 KV  ggml.c:12430-12566, llama.cpp:2303-2335
-//   k_attn      K·q (fp16 operands, fp32 acc) → scale → causal mask → fp16-table softmax (fp64 sum) → P→fp16 → V·P
-//               llama.cpp:2337-2400, ggml.c:11031 (F16 path), 11390, 11925-11973, 12009-12078
+//   k_attn      K·q (fp16 operands, fp32 acc) → scale → causal mask → fp16-table softmax (fp64 sum) → P→fp16 → V·P, with
+//               the reference's AVX2 f16-dot lane order so the result is bit-exact
+//               llama.cpp:2337-2400, ggml.c:11031 (F16 path), 2392-2426, 11390, 11925-11973, 12009-12078
 //   k_argmax    greedy pick on device (used by the fused decode loop; ties → lowest id)
 #pragma once
 #include "device_types.cuh"
@@ -71,41 +72,66 @@ static __global__ void k_embed(const uint8_t* table, int type, size_t row_bytes,
 }
 
 // ---------------------------------------------------------------------------------------- rope+kv
+// KV cache layouts (ours; the reference keeps K [n_ctx][n_embd_gqa] and V transposed [n_embd_gqa][n_ctx], llama.cpp:2323-2335).
+// Both are permuted so that the GPU lane that plays lane L of the reference's 4x8-lane f16 dot (ggml_vec_dot_f16,
+// ggml.c:2392-2426: lane L accumulates elements 32i+L in order i) finds ITS elements contiguous:
+//   K: [n_ctx][n_kv][hd]        element e of a head row is stored at (e & 31) * (hd/32) + (e >> 5)
+//   V: [n_kv][hd][ctx_pad]      (channel-major like the reference) position t at (t & ~255) + (t & 31) * 8 + ((t >> 5) & 7)
+__host__ __device__ inline int kv_ctx_pad(int n_ctx) { return (n_ctx + 255) & ~255; }
+__host__ __device__ inline int k_perm(int e, int hd) { return (e & 31) * (hd >> 5) + (e >> 5); }
+__host__ __device__ inline int v_perm(int t) { return (t & ~255) + (t & 31) * 8 + ((t >> 5) & 7); }
+
 struct RopeKVParams {
   float* q;             // [N][n_head*hd]   rotated in place
   const float* k;       // [N][n_kv*hd]
   const float* v;       // [N][n_kv*hd]
-  uint16_t* kc;         // this layer's K cache [n_ctx][n_kv*hd] fp16 (RoPE'd K, llama.cpp:2333)
-  uint16_t* vc;         // this layer's V cache [n_kv][n_ctx][hd] fp16
+  uint16_t* kc;         // this layer's K cache (RoPE'd K, llama.cpp:2333)
+  uint16_t* vc;         // this layer's V cache
   const float2* rope;   // [n_ctx][hd/2] (cos, sin), built on the host with libm exactly like the reference loop
-  const int* n_past;    // device scalar
+  const int* state;     // device: {token, position, step, n_total}
   int n_head, n_kv, hd, n_ctx, neox;
   int q_stride, kv_stride;   // row strides (floats) of q and k/v — falcon reads them out of one fused qkv row
 };
 
+// RoPE of one pair.  mode 0 (llama): x0*c*zeta - x1*s*zeta with the run-time zeta == 1.0f — four separately rounded
+// products, no fusion (ggml.c:12521-12539).  neox (falcon): the reference binary contracts the source's x0*c - x1*s and
+// x0*s + x1*c into vfmsub231ss / vfmadd132ss (ggml.c:12540-12561 as compiled by gcc -O3 -mfma); verified against the
+// compiled reference through ggml_rope_custom_inplace.
+__device__ __forceinline__ void rope_pair(float x0, float x1, float2 cs, int neox, float& o0, float& o1) {
+  if (neox) {
+    o0 = __fmaf_rn(x0, cs.x, -__fmul_rn(x1, cs.y));
+    o1 = __fmaf_rn(x0, cs.y, __fmul_rn(x1, cs.x));
+  } else {
+    o0 = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
+    o1 = __fadd_rn(__fmul_rn(x0, cs.y), __fmul_rn(x1, cs.x));
+  }
+}
+
 // grid = (N, n_head + n_kv), block = hd/2
 static __global__ void k_rope_kv(const RopeKVParams p) {
   const int n = blockIdx.x, hh = blockIdx.y, i = threadIdx.x;
-  const int pos = *p.n_past + n;
+  const int pos = p.state[1] + n;
   if (pos >= p.n_ctx) return;
   const float2 cs = p.rope[(size_t)pos * (p.hd / 2) + i];
   const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + p.hd / 2 : 2 * i + 1;
   if (hh < p.n_head) {
     float* qh = p.q + (size_t)n * p.q_stride + (size_t)hh * p.hd;
-    const float x0 = qh[i0], x1 = qh[i1];
-    qh[i0] = __fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y));
-    qh[i1] = __fadd_rn(__fmul_rn(x0, cs.y), __fmul_rn(x1, cs.x));
+    float o0, o1;
+    rope_pair(qh[i0], qh[i1], cs, p.neox, o0, o1);
+    qh[i0] = o0; qh[i1] = o1;
   } else {
     const int kh = hh - p.n_head;
     const float* ksrc = p.k + (size_t)n * p.kv_stride + (size_t)kh * p.hd;
     const float* vsrc = p.v + (size_t)n * p.kv_stride + (size_t)kh * p.hd;
-    const float x0 = ksrc[i0], x1 = ksrc[i1];
-    uint16_t* kd = p.kc + (size_t)pos * (p.n_kv * p.hd) + (size_t)kh * p.hd;
-    kd[i0] = f2h(__fsub_rn(__fmul_rn(x0, cs.x), __fmul_rn(x1, cs.y)));
-    kd[i1] = f2h(__fadd_rn(__fmul_rn(x0, cs.y), __fmul_rn(x1, cs.x)));
-    uint16_t* vd = p.vc + ((size_t)kh * p.n_ctx + pos) * p.hd;
-    vd[2 * i] = f2h(vsrc[2 * i]);
-    vd[2 * i + 1] = f2h(vsrc[2 * i + 1]);
+    float o0, o1;
+    rope_pair(ksrc[i0], ksrc[i1], cs, p.neox, o0, o1);
+    uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kh) * p.hd;
+    kd[k_perm(i0, p.hd)] = f2h(o0);
+    kd[k_perm(i1, p.hd)] = f2h(o1);
+    const int cp = kv_ctx_pad(p.n_ctx);
+    uint16_t* vd = p.vc + (size_t)kh * p.hd * cp + v_perm(pos);
+    vd[(size_t)(2 * i) * cp] = f2h(vsrc[2 * i]);
+    vd[(size_t)(2 * i + 1) * cp] = f2h(vsrc[2 * i + 1]);
   }
 }
 
@@ -116,7 +142,7 @@ struct AttnParams {
   const uint16_t* vc;    // layer V cache
   float* out;            // [N][n_head*hd]
   const uint16_t* exp_tab;
-  const int* n_past;
+  const int* state;      // device: {token, position, step, n_total}
   float kq_scale;
   int n_head, n_kv, hd, n_ctx, q_stride;
 };
@@ -124,49 +150,66 @@ struct AttnParams {
 constexpr int ATTN_THREADS = 256;
 constexpr int ATTN_WARPS = ATTN_THREADS / 32;
 
-// grid = (n_head, N); dynamic smem = attn_smem_bytes(n_ctx, hd)
+__host__ __device__ inline size_t attn_smem_bytes(int n_ctx, int hd) {
+  return (size_t)kv_ctx_pad(n_ctx) * 6 + (size_t)hd * 2 + (size_t)hd * 4;
+}
+
+// GGML_F32x8_REDUCE over a warp that plays 4 accumulators x 8 lanes (lane = 8*j + l) — ggml.c:1964-1982
+__device__ __forceinline__ float attn_reduce_f32x8(float v) {
+  v = v + __shfl_xor_sync(0xffffffffu, v, 16);
+  v = v + __shfl_xor_sync(0xffffffffu, v, 8);
+  v = v + __shfl_xor_sync(0xffffffffu, v, 4);
+  v = v + __shfl_xor_sync(0xffffffffu, v, 1);
+  v = v + __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+
+// One query token (blockIdx.y) of one head (blockIdx.x), bit-exact with the reference's attention block:
+//   KQ  = ggml_vec_dot_f16(hd, K row, f16(q))  — lane L: fma over elements 32i+L in order, then the 4x8 reduce
+//   KQ *= kq_scale; causal mask; soft_max: max, fp16 exp table, fp64 sum (exact), * (float)(1/sum)   (ggml.c:12047-12069)
+//   KQV = ggml_vec_dot_f16(n_total, V^T row, f16(P)): the first n_total & ~31 positions through the 32 lanes, the rest added
+//         one by one in double — n_total = n_past + N of the eval call the token belongs to (that is the row length the
+//         reference's mul_mat sees, llama.cpp:2373-2385), so results match the reference for the same batch_size chunking.
 static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red_f[ATTN_WARPS];
   __shared__ double red_d[ATTN_WARPS];
   const int h = blockIdx.x, n = blockIdx.y;
-  const int hd = p.hd;
-  const int T = min(*p.n_past + n + 1, p.n_ctx);
+  const int hd = p.hd, per = hd >> 5;
+  const int T = min(p.state[1] + n + 1, p.n_ctx);
+  const int n_total = max(T, min(p.state[3], p.n_ctx));
+  const int n_vec = n_total & ~31;
   const int kvh = h / (p.n_head / p.n_kv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp = kv_ctx_pad(p.n_ctx);
 
-  const size_t ctx_pad = ((size_t)p.n_ctx + 7) & ~(size_t)7;   // keeps every sub-array 16-byte aligned for any n_ctx
-  float* sc = (float*)smem;                                  // [ctx_pad]
-  uint16_t* p16 = (uint16_t*)(smem + ctx_pad * 4);           // [ctx_pad]
-  uint16_t* q16 = p16 + ctx_pad;                             // [hd]
-  float* part = (float*)(smem + ctx_pad * 6 + (size_t)hd * 2);   // [ATTN_WARPS][hd]
+  float* sc = (float*)smem;                          // [cp] scores, then exp values
+  uint16_t* p16 = (uint16_t*)(smem + (size_t)cp * 4);   // [cp] f16 probabilities, V-permuted order
+  uint16_t* q16 = p16 + cp;                          // [hd] f16 query, K-permuted order
+  float* vres = (float*)(q16 + hd);                  // [hd] lane-part results of V·P
 
   const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
-  for (int i = threadIdx.x; i < hd; i += ATTN_THREADS) q16[i] = f2h(qv[i]);
+  for (int e = threadIdx.x; e < hd; e += ATTN_THREADS) q16[k_perm(e, hd)] = f2h(qv[e]);
   __syncthreads();
 
-  // scores: one warp per cached position
-  const int per = hd / 32;   // halves per lane (2 or 4; hd is 64 or 128)
-  const size_t krow = (size_t)p.n_kv * hd;
   for (int t = warp; t < T; t += ATTN_WARPS) {
-    const uint16_t* kr = p.kc + (size_t)t * krow + (size_t)kvh * hd + lane * per;
-    float acc = 0.f;
+    const uint16_t* kr = p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * per;
+    float s = 0.f;
     if (per == 4) {
       const uint2 kk = *(const uint2*)kr;
       const uint2 qq = *(const uint2*)(q16 + lane * 4);
-      acc = fmaf(h2f((uint16_t)(kk.x & 0xffff)), h2f((uint16_t)(qq.x & 0xffff)), acc);
-      acc = fmaf(h2f((uint16_t)(kk.x >> 16)), h2f((uint16_t)(qq.x >> 16)), acc);
-      acc = fmaf(h2f((uint16_t)(kk.y & 0xffff)), h2f((uint16_t)(qq.y & 0xffff)), acc);
-      acc = fmaf(h2f((uint16_t)(kk.y >> 16)), h2f((uint16_t)(qq.y >> 16)), acc);
+      s = __fmaf_rn(h2f((uint16_t)(kk.x & 0xffff)), h2f((uint16_t)(qq.x & 0xffff)), s);
+      s = __fmaf_rn(h2f((uint16_t)(kk.x >> 16)), h2f((uint16_t)(qq.x >> 16)), s);
+      s = __fmaf_rn(h2f((uint16_t)(kk.y & 0xffff)), h2f((uint16_t)(qq.y & 0xffff)), s);
+      s = __fmaf_rn(h2f((uint16_t)(kk.y >> 16)), h2f((uint16_t)(qq.y >> 16)), s);
     } else {
-      for (int e = 0; e < per; e++) acc = fmaf(h2f(kr[e]), h2f(q16[lane * per + e]), acc);
+      for (int i = 0; i < per; i++) s = __fmaf_rn(h2f(kr[i]), h2f(q16[lane * per + i]), s);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) sc[t] = __fmul_rn(acc, p.kq_scale);
+    s = attn_reduce_f32x8(s);
+    if (lane == 0) sc[t] = __fmul_rn(s, p.kq_scale);
   }
   __syncthreads();
 
-  // softmax (ggml.c:12047-12069)
   float mx = -INFINITY;
   for (int t = threadIdx.x; t < T; t += ATTN_THREADS) mx = fmaxf(mx, sc[t]);
   mx = warp_max(mx);
@@ -188,37 +231,40 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
 #pragma unroll
   for (int w = 0; w < ATTN_WARPS; w++) sum += red_d[w];
   const float inv = (float)(1.0 / sum);
-  for (int t = threadIdx.x; t < T; t += ATTN_THREADS) p16[t] = f2h(__fmul_rn(sc[t], inv));
+  const int t_end = (T + 255) & ~255;
+  for (int t = threadIdx.x; t < t_end; t += ATTN_THREADS) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
   __syncthreads();
 
-  // V·P: warp w covers positions w, w+W, ...; lane owns `per` channels
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const uint16_t* vbase = p.vc + (size_t)kvh * p.n_ctx * hd + lane * per;
-  for (int t = warp; t < T; t += ATTN_WARPS) {
-    const float pt = h2f(p16[t]);
-    const uint16_t* vr = vbase + (size_t)t * hd;
-    if (per == 4) {
-      const uint2 vv = *(const uint2*)vr;
-      acc[0] = fmaf(pt, h2f((uint16_t)(vv.x & 0xffff)), acc[0]);
-      acc[1] = fmaf(pt, h2f((uint16_t)(vv.x >> 16)), acc[1]);
-      acc[2] = fmaf(pt, h2f((uint16_t)(vv.y & 0xffff)), acc[2]);
-      acc[3] = fmaf(pt, h2f((uint16_t)(vv.y >> 16)), acc[3]);
-    } else {
-      for (int e = 0; e < per; e++) acc[e] = fmaf(pt, h2f(vr[e]), acc[e]);
-    }
-  }
-  for (int e = 0; e < per; e++) part[warp * hd + lane * per + e] = acc[e];
-  __syncthreads();
-  for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
+  // V·P, lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i
+  const int lim = min(T, n_vec);
+  const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
+  for (int c = warp; c < hd; c += ATTN_WARPS) {
+    const uint16_t* vrow = vhead + (size_t)c * cp;
     float s = 0.f;
+    for (int ch = 0; ch * 256 < lim; ch++) {
+      const uint4 vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
+      const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
+      const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w}, pw[4] = {pp.x, pp.y, pp.z, pp.w};
 #pragma unroll
-    for (int w = 0; w < ATTN_WARPS; w++) s += part[w * hd + c];
-    p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = s;
+      for (int i = 0; i < 8; i++) {
+        const int t = ch * 256 + 32 * i + lane;
+        if (t < lim) {
+          const uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff), ph = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          s = __fmaf_rn(h2f(vh), h2f(ph), s);
+        }
+      }
+    }
+    s = attn_reduce_f32x8(s);
+    if (lane == 0) vres[c] = s;
   }
-}
-
-__host__ inline size_t attn_smem_bytes(int n_ctx, int hd) {
-  return (((size_t)n_ctx + 7) & ~(size_t)7) * 6 + (size_t)hd * 2 + (size_t)ATTN_WARPS * hd * 4;
+  __syncthreads();
+  // leftover part: positions n_vec <= t < T one by one in double (ggml.c:2415-2418), one thread per channel
+  for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
+    double sumf = (double)vres[c];
+    const uint16_t* vrow = vhead + (size_t)c * cp;
+    for (int t = n_vec; t < T; t++) sumf += (double)__fmul_rn(h2f(vrow[v_perm(t)]), h2f(p16[v_perm(t)]));
+    p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = (float)sumf;
+  }
 }
 
 // ----------------------------------------------------------------------------------------- argmax

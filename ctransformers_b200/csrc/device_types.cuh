@@ -15,7 +15,8 @@
 //   F32    K x 4 B                     -                    -                                 -
 //
 // Block contents are exactly the reference's (k_quants.h:76-117, ggml.c:888-925); only their placement
-// changes.  Activations are quantized on the fly to the reference's Q8_K / Q8_0 (bit-exact) into
+// changes.  Inside each K-quant block the 32-bit words of qs/qh are additionally stored lane-major
+// (repack.cuh) so that the GPU lane that plays AVX2 lane l fetches all its words with one 16-byte load.  Activations are quantized on the fly to the reference's Q8_K / Q8_0 (bit-exact) into
 // shared memory (struct ActView) and never touch HBM.
 #pragma once
 #include <cstdint>

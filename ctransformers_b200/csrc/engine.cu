@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "repack.cuh"
+#include "tables.hpp"
 
 namespace ctb {
 
@@ -23,12 +24,14 @@ namespace ctb {
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // advance the on-device decode state after a greedy pick: state = {token, n_past, step}
-__global__ void k_advance(const int* pick, int* state, int* out_tokens) {
-  const int t = *pick;
+// state = {token, position, step, n_total}; pick lives in state[4]
+__global__ void k_advance(int* state, int* out_tokens) {
+  const int t = state[4];
   out_tokens[state[2]] = t;
   state[0] = t;
   state[1] += 1;
   state[2] += 1;
+  state[3] = state[1] + 1;   // a single-token eval: the attention rows have length position + 1
 }
 
 static bool supported_matrix_type(uint32_t t) {
@@ -45,7 +48,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   size_t total = 0;
   for (const auto& t : g.tensors) total += align_up(t.nbytes, 256) + 4 * 256;   // up to 4 planes, each 256-aligned
   total += align_up(max_raw_tensor_bytes(g), 256);                              // raw staging for the repack
-  const size_t kv = (size_t)hp.n_layer * hp.n_ctx * hp.n_embd_gqa() * 2;
+  const size_t kv = (size_t)hp.n_layer * (hp.n_ctx + 256) * hp.n_embd_gqa() * 2;
   total += 2 * align_up(kv, 256);
   total += 3 * align_up(65536 * 2, 256);
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
@@ -190,8 +193,8 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
     std::vector<uint16_t> silu(65536), gelu(65536), ex(65536);
     for (int i = 0; i < 65536; i++) {
       const float f = host_h2f((uint16_t)i);
-      silu[i] = host_f2h(f / (1.0f + expf(-f)));
-      gelu[i] = host_f2h(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f))));
+      silu[i] = host_f2h(host_silu(f));
+      gelu[i] = host_f2h(host_gelu(f));
       ex[i] = host_f2h(expf(f));
     }
     silu_tab_ = (uint16_t*)alloc(65536 * 2); gelu_tab_ = (uint16_t*)alloc(65536 * 2); exp_tab_ = (uint16_t*)alloc(65536 * 2);
@@ -216,10 +219,11 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   }
   // ---- KV cache + workspace
   const size_t kv = (size_t)hp_.n_layer * hp_.n_ctx * hp_.n_embd_gqa();
+  const size_t vv = (size_t)hp_.n_layer * kv_ctx_pad(hp_.n_ctx) * hp_.n_embd_gqa();
   kc_ = (uint16_t*)alloc(kv * 2);
-  vc_ = (uint16_t*)alloc(kv * 2);
+  vc_ = (uint16_t*)alloc(vv * 2);
   CTB_CUDA(cudaMemset(kc_, 0, kv * 2));
-  CTB_CUDA(cudaMemset(vc_, 0, kv * 2));
+  CTB_CUDA(cudaMemset(vc_, 0, vv * 2));
   const size_t qkv = (size_t)hp_.n_embd + 2 * (size_t)hp_.n_embd_gqa();
   d_state_ = (int*)alloc(64);
   xa_ = (float*)alloc(hp_.n_embd * 4); xb_ = (float*)alloc(hp_.n_embd * 4);
@@ -234,6 +238,10 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
+  {
+    const size_t need = (size_t)std::max(hp_.n_embd, hp_.n_ff) * 4 + 64;   // worst case: f32 activations of the widest input
+    if (need > 48 * 1024) CTB_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+  }
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();
@@ -263,14 +271,11 @@ void Engine::set_stream(cudaStream_t s) {
 void Engine::launch_matvec(MVParams& p) {
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
-  constexpr int R = 2;
   long units = 0;
-  if (p.pair_silu) units = (p.seg[0].w.M + R - 1) / R;
-  else for (int s = 0; s < p.nseg; s++) units += (p.seg[s].w.M + R - 1) / R;
+  if (p.pair_silu) units = (p.seg[0].w.M + MV_ROWS - 1) / MV_ROWS;
+  else for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
   const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)sm_count_ * 8));
-  const size_t smem = act_smem_bytes(p.act, p.K);
-  if (smem > 48 * 1024) CTB_CUDA(cudaFuncSetAttribute(k_matvec<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_matvec<R><<<grid, MV_THREADS, smem, stream_>>>(p);
+  k_matvec<<<grid, MV_THREADS, act_smem_bytes(p.act, p.K), stream_>>>(p);
   launches_per_step_++;
   mark(0);
 }
@@ -295,12 +300,12 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
   for (int il = 0; il < hp_.n_layer; il++) {
     const LayerW& L = layers_[il];
     uint16_t* kc = kc_ + (size_t)il * hp_.n_ctx * gqa;
-    uint16_t* vc = vc_ + (size_t)il * hp_.n_ctx * gqa;
+    uint16_t* vc = vc_ + (size_t)il * gqa * kv_ctx_pad(hp_.n_ctx);
     RopeKVParams rp{};
-    rp.kc = kc; rp.vc = vc; rp.rope = rope_; rp.n_past = d_state_ + 1;
+    rp.kc = kc; rp.vc = vc; rp.rope = rope_; rp.state = d_state_;
     rp.n_head = hp_.n_head; rp.n_kv = n_kv; rp.hd = hd; rp.n_ctx = hp_.n_ctx; rp.neox = hp_.falcon ? 1 : 0;
     AttnParams ap{};
-    ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.n_past = d_state_ + 1; ap.kq_scale = kq_scale;
+    ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.state = d_state_; ap.kq_scale = kq_scale;
     ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx;
 
     if (!hp_.falcon) {
@@ -396,8 +401,8 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
     p.seg[0] = seg(output_, d_logits_);
     launch_matvec(p);
     if (greedy) {
-      k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 3);
-      k_advance<<<1, 1, 0, stream_>>>(d_state_ + 3, d_state_, d_tokens_out_);
+      k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
+      k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
       launches_per_step_ += 2;
     }
   }
@@ -416,7 +421,7 @@ void Engine::mark(int kind) {
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
   CTB_CUDA(cudaSetDevice(device_));
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
-  h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = 0;
+  h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
   const long keep = launches_per_step_;
   profiling_ = true;
@@ -489,7 +494,7 @@ void Engine::eval(const int* tokens, int n, int n_past) {
   CTB_CUDA(cudaEventRecord(ev0_, stream_));
   for (int i = 0; i < n; i++) {
     int* st = h_state_ + (size_t)i * 4;
-    st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = 0;
+    st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = n_past + n;   // n_total: row length of this eval's attention mat-muls
     CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
     CTB_CUDA(cudaGraphLaunch(i == n - 1 ? graph_full_ : graph_nolog_, stream_));
   }
@@ -508,7 +513,7 @@ double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_
   if (n_past + n_steps > hp_.n_ctx) throw std::runtime_error("decode_greedy: would run past the context length");
   CTB_CUDA(cudaSetDevice(device_));
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
-  h_state_[0] = first_token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = 0;
+  h_state_[0] = first_token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
   CTB_CUDA(cudaEventRecord(ev0_, stream_));
   for (int s = 0; s < n_steps; s++) CTB_CUDA(cudaGraphLaunch(graph_greedy_, stream_));

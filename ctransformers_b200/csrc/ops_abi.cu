@@ -13,6 +13,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "repack.cuh"
+#include "tables.hpp"
 
 using namespace ctb;
 
@@ -43,8 +44,8 @@ OpsTables& tables() {
     std::vector<uint16_t> s(65536), g(65536), e(65536);
     for (int i = 0; i < 65536; i++) {
       const float f = __half2float(__ushort_as_half((uint16_t)i));
-      s[i] = __half_as_ushort(__float2half_rn(f / (1.0f + expf(-f))));
-      g[i] = __half_as_ushort(__float2half_rn(0.5f * f * (1.0f + tanhf(0.79788456080286535587989211986876f * f * (1.0f + 0.044715f * f * f)))));
+      s[i] = __half_as_ushort(__float2half_rn(host_silu(f)));
+      g[i] = __half_as_ushort(__float2half_rn(host_gelu(f)));
       e[i] = __half_as_ushort(__float2half_rn(expf(f)));
     }
     OPS_CUDA(cudaMalloc(&t.silu, 65536 * 2)); OPS_CUDA(cudaMalloc(&t.gelu, 65536 * 2)); OPS_CUDA(cudaMalloc(&t.ex, 65536 * 2));
@@ -87,17 +88,21 @@ void upload(OwnedMat& o, int type, const void* blocks, int K, int M) {
   o.m.qs = (const uint8_t*)pl[0]; o.m.qh = (const uint8_t*)pl[1]; o.m.sc = (const uint8_t*)pl[2]; o.m.d = pl[3];
 }
 
+long matvec_units(const MVParams& p) {
+  if (p.pair_silu) return (p.seg[0].w.M + MV_ROWS - 1) / MV_ROWS;
+  long units = 0;
+  for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
+  return units;
+}
+
 void run_matvec(MVParams& p) {
-  constexpr int R = 2;
   p.silu_tab = tables().silu;
   p.gelu_tab = tables().gelu;
-  long units = 0;
-  if (p.pair_silu) units = (p.seg[0].w.M + R - 1) / R;
-  else for (int s = 0; s < p.nseg; s++) units += (p.seg[s].w.M + R - 1) / R;
+  const long units = matvec_units(p);
   const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, 148L * 8));
   const size_t smem = act_smem_bytes(p.act, p.K);
-  if (smem > 48 * 1024) OPS_CUDA(cudaFuncSetAttribute(k_matvec<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_matvec<R><<<grid, MV_THREADS, smem>>>(p);
+  if (smem > 48 * 1024) OPS_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_matvec<<<grid, MV_THREADS, smem>>>(p);
   OPS_CUDA(cudaGetLastError());
 }
 
@@ -170,7 +175,10 @@ int ctb_quantize_row_q8_K(const float* x, void* y, int k) {
     uint8_t* out = (uint8_t*)y;   // block_q8_K: float d; int8 qs[256]; int16 bsums[16]  (k_quants.h:121-125)
     for (int b = 0; b < nb; b++) {
       memcpy(out + (size_t)b * 292, d + b, 4);
-      memcpy(out + (size_t)b * 292 + 4, dump.data() + (size_t)b * 256, 256);
+      for (int e = 0; e < 256; e++) {   // undo the lane-major shared-memory order (matvec.cuh q8k_word_offset)
+        const int wd = e >> 2, sb = wd >> 3, ln = wd & 7;
+        out[(size_t)b * 292 + 4 + e] = dump[(size_t)((b * 2 + (sb >> 2)) * 8 + ln) * 16 + (sb & 3) * 4 + (e & 3)];
+      }
       memcpy(out + (size_t)b * 292 + 260, bs + (size_t)b * 16, 32);
     }
   });
@@ -210,36 +218,45 @@ int ctb_rope(float* x, int n_heads, int head_dim, int pos, int mode, float freq_
       for (int i = 0; i < half; i++) { tab[(size_t)p * half + i] = make_float2(cosf(theta), sinf(theta)); theta *= theta_scale; }
     }
     const size_t nq = (size_t)n_heads * head_dim;
-    DevBuf dq(nq * 4), dk(nq * 4), dtab(tab.size() * 8), dkc((size_t)(pos + 1) * head_dim * 2), dvc((size_t)(pos + 1) * head_dim * 2), dn(4);
+    DevBuf dq(nq * 4), dtab(tab.size() * 8), dst(16);
     OPS_CUDA(cudaMemcpy(dq.p, x, nq * 4, cudaMemcpyHostToDevice));
-    OPS_CUDA(cudaMemcpy(dk.p, x, nq * 4, cudaMemcpyHostToDevice));
     OPS_CUDA(cudaMemcpy(dtab.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
-    OPS_CUDA(cudaMemcpy(dn.p, &pos, 4, cudaMemcpyHostToDevice));
+    const int st[4] = {0, pos, 0, pos + 1};
+    OPS_CUDA(cudaMemcpy(dst.p, st, 16, cudaMemcpyHostToDevice));
     RopeKVParams rp{};
-    rp.q = dq.as<float>(); rp.k = dk.as<float>(); rp.v = dk.as<float>(); rp.kc = dkc.as<uint16_t>(); rp.vc = dvc.as<uint16_t>();
-    rp.rope = dtab.as<float2>(); rp.n_past = dn.as<int>(); rp.n_head = n_heads; rp.n_kv = 1; rp.hd = head_dim; rp.n_ctx = pos + 1;
-    rp.neox = (mode & 2) ? 1 : 0; rp.q_stride = (int)nq; rp.kv_stride = (int)nq;
-    k_rope_kv<<<dim3(1, n_heads), half>>>(rp);   // only the Q heads (grid.y == n_head ⇒ no KV block)
+    rp.q = dq.as<float>(); rp.rope = dtab.as<float2>(); rp.state = dst.as<int>(); rp.n_head = n_heads; rp.n_kv = 1; rp.hd = head_dim;
+    rp.n_ctx = pos + 1; rp.neox = (mode & 2) ? 1 : 0; rp.q_stride = (int)nq; rp.kv_stride = (int)nq;
+    k_rope_kv<<<dim3(1, n_heads), half>>>(rp);   // grid.y == n_head: only the Q-head blocks exist, no KV store happens
     OPS_CUDA(cudaGetLastError());
     OPS_CUDA(cudaMemcpy(x, dq.p, nq * 4, cudaMemcpyDeviceToHost));
   });
 }
 
 int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache, float* out, int n_head, int n_kv, int head_dim, int T,
-                  float kq_scale) {
+                  int n_total, float kq_scale) {
   return guarded("ctb_attention", [&] {
     if (head_dim != 64 && head_dim != 128) throw std::runtime_error("head_dim must be 64 or 128");
-    const size_t nq = (size_t)n_head * head_dim, nkv = (size_t)T * n_kv * head_dim;
-    DevBuf dq(nq * 4), dk(nkv * 2), dv(nkv * 2), dout(nq * 4), dn(4);
+    if (n_total < T) n_total = T;
+    const int cp = kv_ctx_pad(n_total);
+    const size_t nq = (size_t)n_head * head_dim;
+    // reference layouts in (K [T][n_kv*hd], V transposed [n_kv*hd][T]) -> our permuted device layouts
+    std::vector<uint16_t> kp((size_t)n_total * n_kv * head_dim, 0), vp((size_t)n_kv * head_dim * cp, 0);
+    for (int t = 0; t < T; t++)
+      for (int kh = 0; kh < n_kv; kh++)
+        for (int e = 0; e < head_dim; e++)
+          kp[((size_t)t * n_kv + kh) * head_dim + k_perm(e, head_dim)] = kcache[((size_t)t * n_kv + kh) * head_dim + e];
+    for (int ch = 0; ch < n_kv * head_dim; ch++)
+      for (int t = 0; t < T; t++) vp[(size_t)ch * cp + v_perm(t)] = vcache[(size_t)ch * T + t];
+    DevBuf dq(nq * 4), dk(kp.size() * 2), dv(vp.size() * 2), dout(nq * 4), dst(16);
     OPS_CUDA(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
-    OPS_CUDA(cudaMemcpy(dk.p, kcache, nkv * 2, cudaMemcpyHostToDevice));
-    OPS_CUDA(cudaMemcpy(dv.p, vcache, nkv * 2, cudaMemcpyHostToDevice));
-    const int n_past = T - 1;
-    OPS_CUDA(cudaMemcpy(dn.p, &n_past, 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dk.p, kp.data(), kp.size() * 2, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dv.p, vp.data(), vp.size() * 2, cudaMemcpyHostToDevice));
+    const int st[4] = {0, T - 1, 0, n_total};
+    OPS_CUDA(cudaMemcpy(dst.p, st, 16, cudaMemcpyHostToDevice));
     AttnParams ap{};
     ap.q = dq.as<float>(); ap.kc = dk.as<uint16_t>(); ap.vc = dv.as<uint16_t>(); ap.out = dout.as<float>(); ap.exp_tab = tables().ex;
-    ap.n_past = dn.as<int>(); ap.kq_scale = kq_scale; ap.n_head = n_head; ap.n_kv = n_kv; ap.hd = head_dim; ap.n_ctx = T; ap.q_stride = (int)nq;
-    const size_t smem = attn_smem_bytes(T, head_dim);
+    ap.state = dst.as<int>(); ap.kq_scale = kq_scale; ap.n_head = n_head; ap.n_kv = n_kv; ap.hd = head_dim; ap.n_ctx = n_total; ap.q_stride = (int)nq;
+    const size_t smem = attn_smem_bytes(n_total, head_dim);
     OPS_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
     k_attn<<<dim3(n_head, 1), ATTN_THREADS, smem>>>(ap);
     OPS_CUDA(cudaGetLastError());

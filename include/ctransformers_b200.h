@@ -92,10 +92,13 @@ int ctb_quantize_row_q8_0(const float* x, void* y, int k);
 int ctb_norm(int mode, const float* x, const float* w, const float* b, float* y, int n, float eps);
 /* ggml_rope_custom on [n_heads][head_dim] at position pos; mode 0 or 2 (neox) (ggml.c:12430-12566). */
 int ctb_rope(float* x, int n_heads, int head_dim, int pos, int mode, float freq_base, float freq_scale);
-/* One query token against T cached positions: KQ (fp16 operands) → scale → softmax (fp16 exp table) → V·P.
- * kcache [T][n_kv*hd] fp16, vcache [n_kv][T][hd] fp16, q [n_head*hd] (already rotated), out [n_head*hd]. */
+/* One query token (at position T-1) against T cached positions, all heads, exactly as the reference's attention block:
+ * KQ (fp16 operands) -> scale -> softmax (fp16 exp table) -> V·P.  Caches in the reference's own layouts:
+ * kcache [T][n_kv*hd] fp16 (rotated K), vcache TRANSPOSED [n_kv*hd][T] fp16 (llama.cpp:2323-2335), q [n_head*hd] already
+ * rotated, out [n_head*hd].  n_total = n_past + N of the eval call the token belongs to (>= T): the reference's V·P dot runs
+ * over rows of that length and splits them at n_total & ~31 between its SIMD lanes and a scalar tail. */
 int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache, float* out, int n_head, int n_kv, int head_dim,
-                  int T, float kq_scale);
+                  int T, int n_total, float kq_scale);
 /* silu(W1 x) * (W3 x) with the fp16 SiLU table (ggml.c:3625-3632) — the fused FFN gate. */
 int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const float* x, float* out, int K, int M);
 /* ggml_get_rows on a quantized table (ggml.c:11615-11642). */

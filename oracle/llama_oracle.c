@@ -9,7 +9,9 @@
  * built from the per-op restatements in ggml_oracle.c (each cites its own reference lines).  Token by token:
  * the reference evaluates a batch of N tokens with exactly the same per-token arithmetic (every src1 row is quantized
  * and dotted independently, ggml.c:11141-11244; attention row n sees positions <= n_past+n, ggml.c:11925-11973),
- * so a sequential restatement produces the same numbers up to fp32 summation order inside vec_dot.
+ * so a sequential restatement produces the same numbers — provided each token's V·P dot is taken over the n_past + N
+ * columns of ITS eval call (the f16 dot's SIMD/scalar split depends on that length), which orc_eval does: call it with the
+ * same token chunks the reference's BatchEval uses (llm.h:40-54).
  *
  * KV cache layout follows the reference: K [layer][n_ctx][n_embd_gqa] fp16 (llama.cpp:2323), V transposed
  * [layer][n_embd_gqa][n_ctx] fp16 (llama.cpp:2327-2329).
@@ -31,8 +33,8 @@ void orc_layer_norm_mul_add(const float *x, const float *w, const float *b, floa
 void orc_rope(float *x, int n_heads, int head_dim, int p, int mode, float freq_base, float freq_scale);
 void orc_silu(const float *x, float *y, int n);
 void orc_gelu(const float *x, float *y, int n);
-void orc_attn_head(const float *q, const uint16_t *kcache, size_t k_stride, const uint16_t *vcache, size_t v_stride,
-                   int head_dim, int T, float kq_scale, float *out);
+void orc_attn_head_n(const float *q, const uint16_t *kcache, size_t k_stride, const uint16_t *vcache, size_t v_stride,
+                     int head_dim, int T, int n_total, float kq_scale, float *out);
 void orc_dequantize_row_q4_0(const void *vx, float *y, int k);
 void orc_dequantize_row_q8_0(const void *vx, float *y, int k);
 void orc_dequantize_row_q4_K(const void *vx, float *y, int k);
@@ -126,7 +128,7 @@ static void matvec(const orc_mat *w, const float *x, float *y) {
 }
 
 /* One token at absolute position pos.  x: [n_embd] residual stream in/out. */
-static void eval_token(orc_model *m, int token, int pos, int want_out, float *logits, float *embd) {
+static void eval_token(orc_model *m, int token, int pos, int n_total, int want_out, float *logits, float *embd) {
     const int E = m->n_embd, H = m->n_head, HK = m->n_head_kv, hd = E / H, G = hd * HK, FF = m->n_ff, C = m->n_ctx;
     const float kq_scale = 1.0f / sqrtf((float)E / (float)H);   /* llama.cpp:2260-2264 */
     float *x = (float *)malloc(sizeof(float) * E), *nrm = (float *)malloc(sizeof(float) * E), *nrm2 = (float *)malloc(sizeof(float) * E);
@@ -158,7 +160,7 @@ static void eval_token(orc_model *m, int token, int pos, int want_out, float *lo
         }
         for (int h = 0; h < H; h++) {
             const int kh = h / (H / HK);                                  /* ggml.c:11067-11069 broadcast */
-            orc_attn_head(q + (size_t)h * hd, kc + (size_t)kh * hd, (size_t)G, vc + (size_t)kh * hd * C, (size_t)C, hd, pos + 1, kq_scale, att + (size_t)h * hd);
+            orc_attn_head_n(q + (size_t)h * hd, kc + (size_t)kh * hd, (size_t)G, vc + (size_t)kh * hd * C, (size_t)C, hd, pos + 1, n_total, kq_scale, att + (size_t)h * hd);
         }
         if (want_out && m->trace_attn) memcpy(m->trace_attn + (size_t)il * E, att, sizeof(float) * E);
         if (!m->falcon) {
@@ -193,7 +195,7 @@ int orc_eval(orc_model *m, const int *tokens, int n, int n_past, float *logits, 
     if (n_past + n > m->n_ctx) return -1;
     for (int i = 0; i < n; i++) {
         if (tokens[i] < 0 || tokens[i] >= m->n_vocab) return -2;
-        eval_token(m, tokens[i], n_past + i, i == n - 1, logits, embd);
+        eval_token(m, tokens[i], n_past + i, n_past + n, i == n - 1, logits, embd);
     }
     return 0;
 }

@@ -14,7 +14,7 @@ CASES = {
     "falcon_tiny_q5km": ("falcon", synth.FalconShape(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=1, n_ff=2048, n_layer=2, n_ctx_train=256), "Q5_K_M", 96),
     "falcon_tiny_q4_0": ("falcon", synth.FalconShape(n_vocab=1024, n_embd=256, n_head=4, n_head_kv=1, n_ff=1024, n_layer=2, n_ctx_train=256), "Q4_0", 64),
 }
-PROMPT_LEN = 21
+PROMPT_LEN = 37   # with 24 new tokens the context reaches 61: the f16 dot of V·P then uses its SIMD lanes AND its scalar tail
 N_NEW = 24
 
 

@@ -239,11 +239,14 @@ class OracleModel:
         o.orc_model_set_trace(self.m, ptr(self.trace_layers), ptr(self.trace_attn))
         self.n_past = 0
 
-    def eval(self, tokens):
-        t = np.asarray(tokens, dtype=np.int32)
-        rc = self.o.orc_eval(self.m, ptr(t), len(t), self.n_past, ptr(self.logits), ptr(self.embd))
-        assert rc == 0, rc
-        self.n_past += len(t)
+    def eval(self, tokens, batch_size=8):
+        """Same chunking as the reference's LLM::BatchEval (llm.h:40-54): the chunk an attention row belongs to fixes its length."""
+        toks = np.asarray(tokens, dtype=np.int32)
+        for start in range(0, len(toks), batch_size):
+            t = np.ascontiguousarray(toks[start:start + batch_size])
+            rc = self.o.orc_eval(self.m, ptr(t), len(t), self.n_past, ptr(self.logits), ptr(self.embd))
+            assert rc == 0, rc
+            self.n_past += len(t)
         return self.logits
 
     def __del__(self):

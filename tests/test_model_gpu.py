@@ -2,9 +2,9 @@
 B200 library, against (1) the committed golden fixtures the reference produced (tests/golden/model_*.npz) and (2) the
 unmodified reference itself run live on the same file when oracle/_ref is present.
 
-Bar: last-token logits within 1e-3 relative (max|a-b| / max|b|), greedy token ids identical —
-a mismatch is tolerated only where the reference's own top-2 gap is below 1e-3·|logit| (tie-fragile), reported in the
-assertion message."""
+Bar: the north star asks for logits within 1e-3 relative and identical greedy tokens; the kernels reproduce the
+reference's accumulation order, so these tests demand the stronger thing — logits, embeddings and tokens IDENTICAL to the
+reference's, bit for bit (LOGIT_TOL documents the contractual tolerance and is asserted first for a readable failure)."""
 from pathlib import Path
 
 import numpy as np
@@ -22,12 +22,11 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
 
-def check_tokens(got, want, gaps, ref_logit_scale):
-    for i, (g, w) in enumerate(zip(got, want)):
-        if g != w:
-            assert gaps[i] < LOGIT_TOL * ref_logit_scale, f"step {i}: token {g} != {w} with a clear top-2 gap {gaps[i]:.4g}"
-            return i   # sequences legitimately diverge after a tie; stop comparing
-    return len(want)
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    assert rel_err(a, b) <= LOGIT_TOL, f"outside the contractual tolerance: {rel_err(a, b):.3e}"
+    bad = a.view(np.uint32) != b.view(np.uint32)
+    assert not bad.any(), f"{int(bad.sum())} of {bad.size} values differ from the reference (max rel {rel_err(a, b):.3e})"
 
 
 @pytest.fixture(scope="module")
@@ -46,11 +45,10 @@ def test_against_golden_fixture(name, model_dir):
     path, ctx = modelcases.build(name, model_dir)
     llm = load(path, ctx)
     first_logits, first_embd, toks, last_logits, _ = modelcases.run_greedy(llm, gold["prompt"].tolist(), modelcases.N_NEW)
-    assert rel_err(first_logits, gold["first_logits"]) <= LOGIT_TOL
-    assert rel_err(first_embd, gold["first_embd"]) <= LOGIT_TOL
-    n_same = check_tokens(toks, gold["tokens"].tolist(), gold["gaps"], float(np.abs(gold["first_logits"]).max()))
-    if n_same == len(toks):
-        assert rel_err(last_logits, gold["last_logits"]) <= LOGIT_TOL
+    same_bits(first_logits, gold["first_logits"])
+    same_bits(first_embd, gold["first_embd"])
+    assert toks == gold["tokens"].tolist()
+    same_bits(last_logits, gold["last_logits"])
 
 
 @pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not present")
@@ -58,11 +56,13 @@ def test_against_golden_fixture(name, model_dir):
 def test_against_live_reference(name, model_dir):
     path, ctx = modelcases.build(name, model_dir)
     prompt = modelcases.prompt_for(name)
-    ours = modelcases.run_greedy(load(path, ctx), prompt, modelcases.N_NEW, batch_size=5)
-    theirs = modelcases.run_greedy(load(path, ctx, lib=str(refs.REF_SO), threads=4), prompt, modelcases.N_NEW, batch_size=8)
-    assert rel_err(ours[0], theirs[0]) <= LOGIT_TOL
-    assert rel_err(ours[1], theirs[1]) <= LOGIT_TOL
-    check_tokens(ours[2], theirs[2], theirs[4], float(np.abs(theirs[0]).max()))
+    for bs in (8, 64, 5):   # the chunking is part of the contract: it fixes the row length of the attention mat-muls
+        ours = modelcases.run_greedy(load(path, ctx), prompt, modelcases.N_NEW, batch_size=bs)
+        theirs = modelcases.run_greedy(load(path, ctx, lib=str(refs.REF_SO), threads=4), prompt, modelcases.N_NEW, batch_size=bs)
+        same_bits(ours[0], theirs[0])
+        same_bits(ours[1], theirs[1])
+        assert ours[2] == theirs[2]
+        same_bits(ours[3], theirs[3])
 
 
 @pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not present")
@@ -75,8 +75,8 @@ def test_real_quantized_weights_against_live_reference(model_dir):
     prompt = [1] + np.random.default_rng(0).integers(259, 1024, 30).tolist()
     ours = modelcases.run_greedy(load(path, 64), prompt, 8)
     theirs = modelcases.run_greedy(load(path, 64, lib=str(refs.REF_SO), threads=4), prompt, 8)
-    assert rel_err(ours[0], theirs[0]) <= LOGIT_TOL
-    check_tokens(ours[2], theirs[2], theirs[4], float(np.abs(theirs[0]).max()))
+    same_bits(ours[0], theirs[0])
+    assert ours[2] == theirs[2]
 
 
 def test_logits_are_a_mutable_view_and_sampling_sees_edits(model_dir):
@@ -108,15 +108,18 @@ def test_prefix_reuse_and_kv_overwrite(model_dir):
     assert np.array_equal(np.array(a.logits), np.array(b.logits))
 
 
-def test_batch_size_does_not_change_results(model_dir):
-    path, ctx = modelcases.build("llama_gqa_q5km", model_dir)
-    prompt = modelcases.prompt_for("llama_gqa_q5km")
-    outs = []
-    for bs in (1, 8, 64):
+def test_every_chunking_matches_the_oracle(model_dir):
+    """Like the reference, results depend (in the last bits) on how a prompt is chunked, because a chunk's n_past + N is the
+    row length of its attention mat-muls.  Every chunking must equal the whole-model oracle run with the same chunking."""
+    name = "llama_gqa_q5km"
+    path, ctx = modelcases.build(name, model_dir)
+    prompt = np.random.default_rng(4).integers(259, 2048, 70).tolist()
+    for bs in (1, 8, 33, 64):
         llm = load(path, ctx)
         llm.eval(prompt, batch_size=bs)
-        outs.append(np.array(llm.logits))
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+        m = refs.OracleModel(path, ctx)
+        want = m.eval(prompt, batch_size=bs)
+        same_bits(np.array(llm.logits, dtype=np.float32), want)
 
 
 def test_fused_greedy_decode_matches_stepwise(model_dir, lib):

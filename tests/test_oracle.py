@@ -138,3 +138,24 @@ def test_full_eval_matches_reference_golden(name, tmp_path_factory):
         toks.append(t)
         m.eval([t])
     assert toks == gold["tokens"][:6].tolist()
+
+
+@pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["llama_tiny_q4km", "falcon_tiny_q5km"])
+def test_full_eval_matches_live_reference_for_any_chunking(name, tmp_path_factory):
+    """70-token prompt (so the V·P f16 dot uses both its SIMD part and its scalar tail), three chunkings, then 3 decode steps."""
+    from ctransformers_b200 import AutoModelForCausalLM
+    path, ctx = modelcases.build(name, tmp_path_factory.mktemp("orc_live"))
+    arch, shape, _, _ = modelcases.CASES[name]
+    ids = np.random.default_rng(9).integers(259 if arch == "llama" else 0, shape.n_vocab, 70).tolist()
+    for bs in (8, 64, 33):
+        ref = AutoModelForCausalLM.from_pretrained(str(path), lib=str(refs.REF_SO), context_length=ctx, threads=4)
+        ref.eval(ids, batch_size=bs)
+        m = refs.OracleModel(path, ctx)
+        m.eval(ids, batch_size=bs)
+        for _ in range(3):
+            a = np.array(ref.logits, dtype=np.float32)
+            assert np.array_equal(a.view(np.uint32), m.logits.view(np.uint32))
+            t = int(np.argmax(a))
+            ref.eval([t])
+            m.eval([t])
