@@ -69,19 +69,22 @@ struct ActView {
 
 __host__ __device__ inline size_t act_smem_bytes(int act, int K) {
   switch (act) {
-    case ACT_Q8_K: return (size_t)K + (size_t)(K / 256) * 4 + (size_t)(K / 16) * 2 + 16;
+    case ACT_Q8_K: return (size_t)K + (((size_t)(K / 256) * 4 + 15) & ~(size_t)15) + (size_t)(K / 16) * 2 + 16;
     case ACT_Q8_0: return (size_t)K + (size_t)(K / 32) * 4 + 16;
     case ACT_F16: return (size_t)K * 2;
     default: return (size_t)K * 4;
   }
 }
 
+// bytes reserved for the per-block d values of a Q8_K vector (keeps the bsums that follow 16-byte aligned)
+__host__ __device__ inline size_t q8k_d_bytes(int K) { return ((size_t)(K / 256) * 4 + 15) & ~(size_t)15; }
+
 __device__ __forceinline__ ActView act_view(int act, int K, uint8_t* smem) {
   ActView a;
   a.qs = (const int8_t*)smem;
   const size_t off = ((size_t)K + 15) & ~(size_t)15;
   a.d = (const float*)(smem + off);
-  a.bs = (const int16_t*)(smem + off + (size_t)(K / 256) * 4);
+  a.bs = (const int16_t*)(smem + off + q8k_d_bytes(K));
   return a;
 }
 
@@ -209,7 +212,7 @@ __device__ __forceinline__ void stage_activation(const float* x, const float* nw
     int8_t* qs = (int8_t*)smem;
     const size_t off = ((size_t)K + 15) & ~(size_t)15;
     float* dd = (float*)(smem + off);
-    int16_t* bs = (int16_t*)(smem + off + (size_t)(K / 256) * 4);
+    int16_t* bs = (int16_t*)(smem + off + q8k_d_bytes(K));
     const int nchunk = (K + 255) / 256;   // Q8_K: K % 256 == 0; Q8_0: K % 32 == 0, the last warp-chunk may be partial
     for (int c = warp; c < nchunk; c += MV_WARPS) {
       float v[8];

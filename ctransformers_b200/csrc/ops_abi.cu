@@ -171,7 +171,7 @@ int ctb_quantize_row_q8_K(const float* x, void* y, int k) {
     const int nb = k / 256;
     const size_t off = ((size_t)k + 15) & ~(size_t)15;
     const float* d = (const float*)(dump.data() + off);
-    const int16_t* bs = (const int16_t*)(dump.data() + off + (size_t)nb * 4);
+    const int16_t* bs = (const int16_t*)(dump.data() + off + q8k_d_bytes(k));
     uint8_t* out = (uint8_t*)y;   // block_q8_K: float d; int8 qs[256]; int16 bsums[16]  (k_quants.h:121-125)
     for (int b = 0; b < nb; b++) {
       memcpy(out + (size_t)b * 292, d + b, 4);
