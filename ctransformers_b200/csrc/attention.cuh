@@ -137,21 +137,25 @@ static __global__ void k_rope_kv(const RopeKVParams p) {
 
 // ------------------------------------------------------------------------------------------- attn
 struct AttnParams {
-  const float* q;        // [N][q_stride] (already rotated)
-  const uint16_t* kc;    // layer K cache
-  const uint16_t* vc;    // layer V cache
+  const float* q;        // [N][q_stride] raw projections (NOT yet rotated)
+  const float* k;        // [N][kv_stride]
+  const float* v;        // [N][kv_stride]
+  uint16_t* kc;          // layer K cache
+  uint16_t* vc;          // layer V cache
   float* out;            // [N][n_head*hd]
   const uint16_t* exp_tab;
+  const float2* rope;    // [n_ctx][hd/2]
   const int* state;      // device: {token, position, step, n_total}
   float kq_scale;
-  int n_head, n_kv, hd, n_ctx, q_stride;
+  int n_head, n_kv, hd, n_ctx, q_stride, kv_stride, neox;
 };
 
-constexpr int ATTN_THREADS = 256;
+constexpr int ATTN_THREADS = 512;
 constexpr int ATTN_WARPS = ATTN_THREADS / 32;
+constexpr int ATTN_CH = 32;   // output channels per CTA
 
 __host__ __device__ inline size_t attn_smem_bytes(int n_ctx, int hd) {
-  return (size_t)kv_ctx_pad(n_ctx) * 6 + (size_t)hd * 2 + (size_t)hd * 4;
+  return (size_t)kv_ctx_pad(n_ctx) * 6 + (size_t)hd * 2 * 3 + (size_t)ATTN_CH * 4;
 }
 
 // GGML_F32x8_REDUCE over a warp that plays 4 accumulators x 8 lanes (lane = 8*j + l) — ggml.c:1964-1982
@@ -164,49 +168,95 @@ __device__ __forceinline__ float attn_reduce_f32x8(float v) {
   return v;
 }
 
-// One query token (blockIdx.y) of one head (blockIdx.x), bit-exact with the reference's attention block:
+// Fused RoPE + KV-cache store + attention for one query token (blockIdx.y), one head (blockIdx.x) and one group of
+// ATTN_CH output channels (blockIdx.z), bit-exact with the reference's attention block:
+//   RoPE on q and k (k_rope table = the reference's cos/sin recurrence), K -> f16 cache, V -> f16 cache  (llama.cpp:2303-2335)
 //   KQ  = ggml_vec_dot_f16(hd, K row, f16(q))  — lane L: fma over elements 32i+L in order, then the 4x8 reduce
 //   KQ *= kq_scale; causal mask; soft_max: max, fp16 exp table, fp64 sum (exact), * (float)(1/sum)   (ggml.c:12047-12069)
 //   KQV = ggml_vec_dot_f16(n_total, V^T row, f16(P)): the first n_total & ~31 positions through the 32 lanes, the rest added
 //         one by one in double — n_total = n_past + N of the eval call the token belongs to (that is the row length the
 //         reference's mul_mat sees, llama.cpp:2373-2385), so results match the reference for the same batch_size chunking.
+// Every CTA of a head recomputes that head's scores (K rows come from L2); the channel groups split the V·P work, which
+// gives n_head * hd/32 CTAs per token instead of n_head.  The CTA with blockIdx.z == 0 of the first head of each KV group
+// writes that group's K row; V channels are written by the CTAs (first head of the group) that own them.  The current
+// position is always taken from the freshly computed k/v, never read back from the cache, so there is no ordering hazard.
 static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float red_f[ATTN_WARPS];
   __shared__ double red_d[ATTN_WARPS];
-  const int h = blockIdx.x, n = blockIdx.y;
+  const int h = blockIdx.x, n = blockIdx.y, cg = blockIdx.z;
   const int hd = p.hd, per = hd >> 5;
-  const int T = min(p.state[1] + n + 1, p.n_ctx);
+  const int pos = p.state[1] + n;
+  if (pos >= p.n_ctx) return;
+  const int T = pos + 1;
   const int n_total = max(T, min(p.state[3], p.n_ctx));
   const int n_vec = n_total & ~31;
-  const int kvh = h / (p.n_head / p.n_kv);
+  const int group = p.n_head / p.n_kv, kvh = h / group;
+  const bool kv_writer = (h % group) == 0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cp = kv_ctx_pad(p.n_ctx);
 
-  float* sc = (float*)smem;                          // [cp] scores, then exp values
+  float* sc = (float*)smem;                             // [cp] scores, then exp values
   uint16_t* p16 = (uint16_t*)(smem + (size_t)cp * 4);   // [cp] f16 probabilities, V-permuted order
-  uint16_t* q16 = p16 + cp;                          // [hd] f16 query, K-permuted order
-  float* vres = (float*)(q16 + hd);                  // [hd] lane-part results of V·P
+  uint16_t* q16 = p16 + cp;                             // [hd] f16 rotated query, K-permuted order
+  uint16_t* k16 = q16 + hd;                             // [hd] f16 rotated key of this position, K-permuted order
+  uint16_t* v16 = k16 + hd;                             // [hd] f16 value of this position, natural order
+  float* vres = (float*)(v16 + hd);                     // [ATTN_CH]
 
-  const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
-  for (int e = threadIdx.x; e < hd; e += ATTN_THREADS) q16[k_perm(e, hd)] = f2h(qv[e]);
+  {  // RoPE (pairs) + f16 conversion of q, k, v for this position
+    const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
+    const float* kv = p.k + (size_t)n * p.kv_stride + (size_t)kvh * hd;
+    const float* vv = p.v + (size_t)n * p.kv_stride + (size_t)kvh * hd;
+    uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kvh) * hd;
+    for (int i = threadIdx.x; i < hd / 2; i += ATTN_THREADS) {
+      const float2 cs = p.rope[(size_t)pos * (hd / 2) + i];
+      const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
+      float o0, o1;
+      rope_pair(qv[i0], qv[i1], cs, p.neox, o0, o1);
+      q16[k_perm(i0, hd)] = f2h(o0); q16[k_perm(i1, hd)] = f2h(o1);
+      rope_pair(kv[i0], kv[i1], cs, p.neox, o0, o1);
+      const uint16_t h0 = f2h(o0), h1 = f2h(o1);
+      k16[k_perm(i0, hd)] = h0; k16[k_perm(i1, hd)] = h1;
+      if (kv_writer && cg == 0) { kd[k_perm(i0, hd)] = h0; kd[k_perm(i1, hd)] = h1; }
+    }
+    for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
+      const uint16_t hv = f2h(vv[c]);
+      v16[c] = hv;
+      if (kv_writer && c / ATTN_CH == cg) p.vc[((size_t)kvh * hd + c) * cp + v_perm(pos)] = hv;
+    }
+  }
   __syncthreads();
 
-  for (int t = warp; t < T; t += ATTN_WARPS) {
-    const uint16_t* kr = p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * per;
-    float s = 0.f;
-    if (per == 4) {
-      const uint2 kk = *(const uint2*)kr;
-      const uint2 qq = *(const uint2*)(q16 + lane * 4);
-      s = __fmaf_rn(h2f((uint16_t)(kk.x & 0xffff)), h2f((uint16_t)(qq.x & 0xffff)), s);
-      s = __fmaf_rn(h2f((uint16_t)(kk.x >> 16)), h2f((uint16_t)(qq.x >> 16)), s);
-      s = __fmaf_rn(h2f((uint16_t)(kk.y & 0xffff)), h2f((uint16_t)(qq.y & 0xffff)), s);
-      s = __fmaf_rn(h2f((uint16_t)(kk.y >> 16)), h2f((uint16_t)(qq.y >> 16)), s);
-    } else {
-      for (int i = 0; i < per; i++) s = __fmaf_rn(h2f(kr[i]), h2f(q16[lane * per + i]), s);
+  if (per == 4) {
+    // 8 cached rows per warp step, all loads issued before the first is used (the loop is latency-bound otherwise)
+    const uint2 qq = *(const uint2*)(q16 + lane * 4);
+    const float q0 = h2f((uint16_t)(qq.x & 0xffff)), q1 = h2f((uint16_t)(qq.x >> 16)), q2 = h2f((uint16_t)(qq.y & 0xffff)), q3 = h2f((uint16_t)(qq.y >> 16));
+    for (int t0 = warp * 8; t0 < T; t0 += ATTN_WARPS * 8) {
+      uint2 kk[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int t = min(t0 + i, T - 1);
+        kk[i] = (t == pos) ? *(const uint2*)(k16 + lane * 4) : *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float s = 0.f;
+        s = __fmaf_rn(h2f((uint16_t)(kk[i].x & 0xffff)), q0, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[i].x >> 16)), q1, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[i].y & 0xffff)), q2, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[i].y >> 16)), q3, s);
+        s = attn_reduce_f32x8(s);
+        if (lane == 0 && t0 + i < T) sc[t0 + i] = __fmul_rn(s, p.kq_scale);
+      }
     }
-    s = attn_reduce_f32x8(s);
-    if (lane == 0) sc[t] = __fmul_rn(s, p.kq_scale);
+  } else {
+    for (int t = warp; t < T; t += ATTN_WARPS) {
+      const uint16_t* kr = (t == pos) ? (k16 + lane * per) : (p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * per);
+      float s = 0.f;
+      for (int i = 0; i < per; i++) s = __fmaf_rn(h2f(kr[i]), h2f(q16[lane * per + i]), s);
+      s = attn_reduce_f32x8(s);
+      if (lane == 0) sc[t] = __fmul_rn(s, p.kq_scale);
+    }
   }
   __syncthreads();
 
@@ -235,11 +285,13 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   for (int t = threadIdx.x; t < t_end; t += ATTN_THREADS) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
   __syncthreads();
 
-  // V·P, lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i
+  // V·P for this CTA's channels.  lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i
   const int lim = min(T, n_vec);
   const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
-  for (int c = warp; c < hd; c += ATTN_WARPS) {
+  for (int cc = warp; cc < ATTN_CH; cc += ATTN_WARPS) {
+    const int c = cg * ATTN_CH + cc;
     const uint16_t* vrow = vhead + (size_t)c * cp;
+    const uint16_t vcur = v16[c];
     float s = 0.f;
     for (int ch = 0; ch * 256 < lim; ch++) {
       const uint4 vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
@@ -249,20 +301,26 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
       for (int i = 0; i < 8; i++) {
         const int t = ch * 256 + 32 * i + lane;
         if (t < lim) {
-          const uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff), ph = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          const uint16_t ph = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          if (t == pos) vh = vcur;
           s = __fmaf_rn(h2f(vh), h2f(ph), s);
         }
       }
     }
     s = attn_reduce_f32x8(s);
-    if (lane == 0) vres[c] = s;
+    if (lane == 0) vres[cc] = s;
   }
   __syncthreads();
   // leftover part: positions n_vec <= t < T one by one in double (ggml.c:2415-2418), one thread per channel
-  for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
-    double sumf = (double)vres[c];
+  for (int cc = threadIdx.x; cc < ATTN_CH; cc += ATTN_THREADS) {
+    const int c = cg * ATTN_CH + cc;
+    double sumf = (double)vres[cc];
     const uint16_t* vrow = vhead + (size_t)c * cp;
-    for (int t = n_vec; t < T; t++) sumf += (double)__fmul_rn(h2f(vrow[v_perm(t)]), h2f(p16[v_perm(t)]));
+    for (int t = n_vec; t < T; t++) {
+      const uint16_t vh = (t == pos) ? v16[c] : vrow[v_perm(t)];
+      sumf += (double)__fmul_rn(h2f(vh), h2f(p16[v_perm(t)]));
+    }
     p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = (float)sumf;
   }
 }

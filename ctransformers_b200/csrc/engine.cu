@@ -238,10 +238,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
-  {
-    const size_t need = (size_t)std::max(hp_.n_embd, hp_.n_ff) * 4 + 64;   // worst case: f32 activations of the widest input
-    if (need > 48 * 1024) CTB_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-  }
+  CTB_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();
@@ -271,11 +268,8 @@ void Engine::set_stream(cudaStream_t s) {
 void Engine::launch_matvec(MVParams& p) {
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
-  long units = 0;
-  if (p.pair_silu) units = (p.seg[0].w.M + MV_ROWS - 1) / MV_ROWS;
-  else for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
-  const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)sm_count_ * 8));
-  k_matvec<<<grid, MV_THREADS, act_smem_bytes(p.act, p.K), stream_>>>(p);
+  const MVLaunch L = matvec_launch_shape(p, sm_count_);
+  k_matvec<<<L.grid, MV_THREADS, L.smem, stream_>>>(p, L.split);
   launches_per_step_++;
   mark(0);
 }
@@ -301,12 +295,9 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
     const LayerW& L = layers_[il];
     uint16_t* kc = kc_ + (size_t)il * hp_.n_ctx * gqa;
     uint16_t* vc = vc_ + (size_t)il * gqa * kv_ctx_pad(hp_.n_ctx);
-    RopeKVParams rp{};
-    rp.kc = kc; rp.vc = vc; rp.rope = rope_; rp.state = d_state_;
-    rp.n_head = hp_.n_head; rp.n_kv = n_kv; rp.hd = hd; rp.n_ctx = hp_.n_ctx; rp.neox = hp_.falcon ? 1 : 0;
     AttnParams ap{};
     ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.state = d_state_; ap.kq_scale = kq_scale;
-    ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx;
+    ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx; ap.rope = rope_; ap.neox = hp_.falcon ? 1 : 0;
 
     if (!hp_.falcon) {
       float* q = qkv_; float* k = qkv_ + n_embd; float* v = qkv_ + n_embd + gqa;
@@ -324,13 +315,10 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
           launch_matvec(p);
         }
       }
-      rp.q = q; rp.k = k; rp.v = v; rp.q_stride = n_embd; rp.kv_stride = gqa;
-      k_rope_kv<<<dim3(1, hp_.n_head + n_kv), hd / 2, 0, stream_>>>(rp);
-      mark(2);
-      ap.q = q; ap.q_stride = n_embd;
-      k_attn<<<dim3(hp_.n_head, 1), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
+      k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
       mark(1);
-      launches_per_step_ += 2;
+      launches_per_step_ += 1;
       {  // wo + residual
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
@@ -372,13 +360,10 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.seg[0] = seg(L.w3, ffn_, EPI_GELU);
         launch_matvec(p);
       }
-      rp.q = q; rp.k = k; rp.v = v; rp.q_stride = qkv_w; rp.kv_stride = qkv_w;
-      k_rope_kv<<<dim3(1, hp_.n_head + n_kv), hd / 2, 0, stream_>>>(rp);
-      mark(2);
-      ap.q = q; ap.q_stride = qkv_w;
-      k_attn<<<dim3(hp_.n_head, 1), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
+      k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
       mark(1);
-      launches_per_step_ += 2;
+      launches_per_step_ += 1;
       {  // attention output projection
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;

@@ -24,9 +24,9 @@
 
 namespace ctb {
 
-constexpr int MV_THREADS = 256;
+constexpr int MV_THREADS = 512;    // one persistent CTA per SM (<= 128 registers per thread): the activation prologue is paid once per SM
 constexpr int MV_WARPS = MV_THREADS / 32;
-constexpr int MV_ROWS = 4;   // quantized weights: rows per warp (one per 8-lane group)
+constexpr int MV_ROWS = 4;   // Q4_0 / Q8_0: rows per warp (one per 8-lane group, in-lane chain)
 constexpr int MV_MAX_SEG = 3;
 
 enum : int { NORM_NONE = 0, NORM_RMS = 1, NORM_LAYER = 2 };
@@ -94,10 +94,21 @@ __device__ __forceinline__ int q8k_word_offset(int b, int s, int l) { return ((b
 // Prologue pieces.  Every float operation is spelled with explicit-rounding intrinsics so nvcc cannot
 // contract a*b+c into an FMA the reference does not perform — and fuses exactly where the reference binary does.
 
-template <typename F>
-__device__ __forceinline__ double block_sum_f64(int K, F f, double* red /* [MV_WARPS] smem */) {
-  double s = 0.0;
-  for (int i = threadIdx.x; i < K; i += MV_THREADS) s += f(i);
+// Whole prologue: normalise + quantize x[K] into shared memory.  All MV_THREADS threads must call.
+// Each thread owns 16 consecutive elements per pass (one bsums group; 16 threads = one Q8_K block, 2 threads = one Q8_0
+// block); all global loads of a pass are issued before anything depends on them.
+__device__ __forceinline__ void load16(const float* p, int valid, float (&v)[16]) {
+  if (valid >= 16) {
+    const float4 a = __ldg((const float4*)p), b = __ldg((const float4*)p + 1), c = __ldg((const float4*)p + 2), d = __ldg((const float4*)p + 3);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y; v[14] = d.z; v[15] = d.w;
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = e < valid ? __ldg(p + e) : 0.f;
+  }
+}
+
+__device__ __forceinline__ double block_sum_f64(double s, double* red /* [MV_WARPS] smem */) {
   s = warp_sum(s);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -108,137 +119,149 @@ __device__ __forceinline__ double block_sum_f64(int K, F f, double* red /* [MV_W
   return t;
 }
 
-struct NormCtx {
-  int mode;
-  float mean;    // LayerNorm only
-  float scale;
-  const float* x;
-  const float* w;
-  const float* b;
-};
-
-__device__ __forceinline__ float norm_apply(const NormCtx& n, int i) {
-  float v = n.x[i];
-  if (n.mode == NORM_NONE) return v;
-  if (n.mode == NORM_LAYER) v = __fsub_rn(v, n.mean);
-  v = __fmul_rn(v, n.scale);
-  if (n.w) v = __fmul_rn(v, n.w[i]);
-  if (n.b) v = __fadd_rn(v, n.b[i]);
-  return v;
+__device__ __forceinline__ uint32_t pack4(const int* q) {
+  return (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
 }
 
-__device__ __forceinline__ NormCtx norm_prepare(int mode, const float* x, const float* w, const float* b, int K, float eps, double* red) {
-  NormCtx n{mode, 0.f, 1.f, x, w, b};
-  if (mode == NORM_RMS) {
-    const double ss = block_sum_f64(K, [&](int i) { float v = x[i]; return (double)__fmul_rn(v, v); }, red);
-    const float mean = (float)(ss / (double)K);
-    n.scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
-  } else if (mode == NORM_LAYER) {
-    const double s = block_sum_f64(K, [&](int i) { return (double)x[i]; }, red);
-    const float mean = (float)(s / (double)K);
-    const double s2 = block_sum_f64(K, [&](int i) { float v = __fsub_rn(x[i], mean); return (double)__fmul_rn(v, v); }, red);
-    const float var = (float)(s2 / (double)K);
-    n.mean = mean;
-    n.scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
-  }
-  return n;
-}
-
-// Q8_K: one warp per 256-element block, lane owns 8 consecutive elements (two int8 words).
-// reference quantize_row_q8_K_reference, k_quants.c:1191-1226: first element with the largest |x| fixes the sign of the
-// scale; iscale = -128/max; q = min(127, nearest_int(iscale*x)); d = 1/iscale; bsums per 16.  nearest_int adds 12582912.f and
-// reads the mantissa — and the reference BINARY fuses iscale*x + 12582912.f into one vfmadd (the loop is auto-vectorised), so
-// the exact product is rounded once.  __fmaf_rn reproduces that.
-__device__ __forceinline__ void quantize_q8k_block(const float (&v)[8], int lane, int b, int8_t* qs_base, float* d_out, int16_t* bs_out /* 16 entries */) {
-  float amax = 0.f, mx = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const float ax = fabsf(v[e]);
-    if (ax > amax) { amax = ax; mx = v[e]; }
-  }
-  const float gmax = warp_max(amax);
-  const int w0 = 2 * lane, w1 = 2 * lane + 1;
-  uint32_t* dst0 = (uint32_t*)(qs_base + q8k_word_offset(b, w0 >> 3, w0 & 7));
-  uint32_t* dst1 = (uint32_t*)(qs_base + q8k_word_offset(b, w1 >> 3, w1 & 7));
-  if (gmax == 0.f) {
-    *dst0 = 0u; *dst1 = 0u;
-    if (lane < 16) bs_out[lane] = 0;
-    if (lane == 0) *d_out = 0.f;
-    return;
-  }
-  const unsigned who = __ballot_sync(0xffffffffu, amax == gmax);
-  const float maxv = __shfl_sync(0xffffffffu, mx, __ffs(who) - 1);
-  const float iscale = __fdiv_rn(-128.f, maxv);
-  int q[8];
-  int sum = 0;
-#pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const float val = __fmaf_rn(iscale, v[e], 12582912.f);
-    q[e] = min(127, (__float_as_int(val) & 0x007fffff) - 0x00400000);
-    sum += q[e];
-  }
-  *dst0 = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
-  *dst1 = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-  sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-  if ((lane & 1) == 0) bs_out[lane >> 1] = (int16_t)sum;
-  if (lane == 0) *d_out = __fdiv_rn(1.f, iscale);
-}
-
-// Q8_0, AVX2 semantics (ggml.c:1232-1268): 4 lanes per 32-element block; d = amax/127 (kept as fp16), id = 127/amax, RNE.
-__device__ __forceinline__ void quantize_q80_group(const float (&v)[8], int lane, bool valid, int8_t* qs_out /* warp's 256-elem base */, float* d_out /* 8 */) {
-  float amax = 0.f;
-#pragma unroll
-  for (int e = 0; e < 8; e++) amax = fmaxf(amax, fabsf(v[e]));
-  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-  amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-  const float d = __fdiv_rn(amax, 127.f);
-  const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
-  int q[8];
-#pragma unroll
-  for (int e = 0; e < 8; e++) q[e] = __float2int_rn(__fmul_rn(v[e], id));
-  uint2 packed;
-  packed.x = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
-  packed.y = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-  if (valid) *(uint2*)(qs_out + lane * 8) = packed;
-  if (valid && (lane & 3) == 0) d_out[lane >> 2] = h2f(f2h(d));   // the reference stores d as fp16 and multiplies with the converted value
-}
-
-// Whole prologue: normalise + quantize x[K] into shared memory.  All MV_THREADS threads must call.
 __device__ __forceinline__ void stage_activation(const float* x, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
                                                   int K, int act, uint8_t* smem, double* red, bool write_norm) {
-  const NormCtx n = norm_prepare(norm_mode, x, nw, nb_, K, eps, red);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (act == ACT_Q8_K || act == ACT_Q8_0) {
-    int8_t* qs = (int8_t*)smem;
-    const size_t off = ((size_t)K + 15) & ~(size_t)15;
-    float* dd = (float*)(smem + off);
-    int16_t* bs = (int16_t*)(smem + off + q8k_d_bytes(K));
-    const int nchunk = (K + 255) / 256;   // Q8_K: K % 256 == 0; Q8_0: K % 32 == 0, the last warp-chunk may be partial
-    for (int c = warp; c < nchunk; c += MV_WARPS) {
-      float v[8];
-      const int base = c * 256 + lane * 8;
+  const int t = threadIdx.x, lane = t & 31;
+  const int passes = (K + MV_THREADS * 16 - 1) / (MV_THREADS * 16);
+  // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
+  float mean = 0.f, scale = 1.f;
+  float v0[16];            // pass 0's elements stay in registers: with K <= 16384 the quantize step needs no second read of x
+  load16(x + t * 16, K - t * 16, v0);
+  if (norm_mode == NORM_RMS) {
+    double ss = 0.0;
+    for (int ps = 0; ps < passes; ps++) {
+      const int base = (ps * MV_THREADS + t) * 16;
+      float v[16];
+      if (ps == 0) {
 #pragma unroll
-      for (int e = 0; e < 8; e++) v[e] = (base + e < K) ? norm_apply(n, base + e) : 0.f;
-      if (write_norm && norm_out) {
+        for (int e = 0; e < 16; e++) v[e] = v0[e];
+      } else load16(x + base, K - base, v);
 #pragma unroll
-        for (int e = 0; e < 8; e++) if (base + e < K) norm_out[base + e] = v[e];
+      for (int e = 0; e < 16; e++) ss += (double)__fmul_rn(v[e], v[e]);
+    }
+    ss = block_sum_f64(ss, red);
+    const float m = (float)(ss / (double)K);
+    scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(m, eps)));
+  } else if (norm_mode == NORM_LAYER) {
+    double s1 = 0.0;
+    for (int ps = 0; ps < passes; ps++) {
+      const int base = (ps * MV_THREADS + t) * 16;
+      float v[16];
+      load16(x + base, K - base, v);
+#pragma unroll
+      for (int e = 0; e < 16; e++) s1 += (double)v[e];
+    }
+    s1 = block_sum_f64(s1, red);
+    mean = (float)(s1 / (double)K);
+    double s2 = 0.0;
+    for (int ps = 0; ps < passes; ps++) {
+      const int base = (ps * MV_THREADS + t) * 16;
+      float v[16];
+      load16(x + base, K - base, v);
+#pragma unroll
+      for (int e = 0; e < 16; e++) { const float d = (base + e < K) ? __fsub_rn(v[e], mean) : 0.f; s2 += (double)__fmul_rn(d, d); }
+    }
+    s2 = block_sum_f64(s2, red);
+    const float var = (float)(s2 / (double)K);
+    scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
+  }
+  // ---- normalise + quantize
+  int8_t* qs = (int8_t*)smem;
+  const size_t off = ((size_t)K + 15) & ~(size_t)15;
+  float* dd = (float*)(smem + off);
+  int16_t* bs = (int16_t*)(smem + off + q8k_d_bytes(K));
+  for (int ps = 0; ps < passes; ps++) {
+    const int base = (ps * MV_THREADS + t) * 16;
+    const int valid = K - base;
+    float v[16];
+    if (ps == 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = v0[e];
+    } else load16(x + base, valid, v);
+    if (norm_mode != NORM_NONE) {
+      float w[16], bb[16];
+      if (nw) load16(nw + base, valid, w);
+      if (nb_) load16(nb_ + base, valid, bb);
+#pragma unroll
+      for (int e = 0; e < 16; e++) {
+        float y = v[e];
+        if (norm_mode == NORM_LAYER) y = __fsub_rn(y, mean);
+        y = __fmul_rn(y, scale);
+        if (nw) y = __fmul_rn(y, w[e]);
+        if (nb_) y = __fadd_rn(y, bb[e]);
+        v[e] = y;
       }
-      if (act == ACT_Q8_K) quantize_q8k_block(v, lane, c, qs, dd + c, bs + c * 16);
-      else quantize_q80_group(v, lane, base < K, qs + c * 256, dd + c * 8);   // all lanes take part in the shuffles
     }
-  } else if (act == ACT_F16) {
-    uint16_t* h = (uint16_t*)smem;
-    for (int i = threadIdx.x; i < K; i += MV_THREADS) {
-      const float v = norm_apply(n, i);
-      if (write_norm && norm_out) norm_out[i] = v;
-      h[i] = f2h(v);
+    if (write_norm && norm_out && valid > 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) if (e < valid) norm_out[base + e] = v[e];
     }
-  } else {
-    float* f = (float*)smem;
-    for (int i = threadIdx.x; i < K; i += MV_THREADS) {
-      const float v = norm_apply(n, i);
-      if (write_norm && norm_out) norm_out[i] = v;
-      f[i] = v;
+    if (act == ACT_Q8_K) {
+      // reference quantize_row_q8_K_reference (k_quants.c:1191-1226): the first element with the largest |x| fixes the sign;
+      // iscale = -128/max; q = min(127, nearest_int(iscale*x)); the reference BINARY fuses iscale*x + 12582912.f (vfmadd), so
+      // the exact product is rounded once — __fmaf_rn.  d = 1/iscale; bsums per 16.  16 lanes (a half-warp) share a block.
+      float amax = 0.f, mx = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; e++) { const float ax = fabsf(v[e]); if (ax > amax) { amax = ax; mx = v[e]; } }
+      float gmax = amax;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) gmax = fmaxf(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+      const unsigned who = __ballot_sync(0xffffffffu, amax == gmax);
+      const int hbase = lane & 16, hl = lane & 15;
+      const unsigned mine = (who >> hbase) & 0xffffu;
+      const float maxv = __shfl_sync(0xffffffffu, mx, hbase + __ffs(mine) - 1);
+      if (valid > 0) {
+        const int b = base >> 8;
+        int q[16];
+        int sum = 0;
+        if (gmax == 0.f) {
+#pragma unroll
+          for (int e = 0; e < 16; e++) q[e] = 0;
+          if (hl == 0) dd[b] = 0.f;
+        } else {
+          const float iscale = __fdiv_rn(-128.f, maxv);
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const float val = __fmaf_rn(iscale, v[e], 12582912.f);
+            q[e] = min(127, (__float_as_int(val) & 0x007fffff) - 0x00400000);
+            sum += q[e];
+          }
+          if (hl == 0) dd[b] = __fdiv_rn(1.f, iscale);
+        }
+        bs[b * 16 + hl] = (int16_t)sum;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int wi = hl * 4 + j;
+          *(uint32_t*)(qs + q8k_word_offset(b, wi >> 3, wi & 7)) = pack4(q + 4 * j);
+        }
+      }
+    } else if (act == ACT_Q8_0) {
+      // quantize_row_q8_0, AVX2 variant (ggml.c:1232-1268): d = amax/127 kept as fp16, id = 127/amax, round-half-even
+      float amax = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; e++) amax = fmaxf(amax, fabsf(v[e]));
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+      if (valid > 0) {
+        const float d = __fdiv_rn(amax, 127.f);
+        const float id = amax != 0.f ? __fdiv_rn(127.f, amax) : 0.f;
+        int q[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) q[e] = __float2int_rn(__fmul_rn(v[e], id));
+        *(uint4*)(qs + base) = make_uint4(pack4(q), pack4(q + 4), pack4(q + 8), pack4(q + 12));
+        if ((lane & 1) == 0) dd[base >> 5] = h2f(f2h(d));
+      }
+    } else if (act == ACT_F16) {
+      uint16_t* h = (uint16_t*)smem;
+#pragma unroll
+      for (int e = 0; e < 16; e++) if (e < valid) h[base + e] = f2h(v[e]);
+    } else {
+      float* f = (float*)smem;
+#pragma unroll
+      for (int e = 0; e < 16; e++) if (e < valid) f[base + e] = v[e];
     }
   }
   __syncthreads();
@@ -268,133 +291,260 @@ __device__ __forceinline__ void unpack_k4(uint32_t s0, uint32_t s1, uint32_t s2,
 }
 #define CTB_BYTE(w, i) ((int)(((w) >> ((i) * 8)) & 0xffu))
 
-// Each dot_* returns the finished row value (valid in every lane of the 8-lane group).  `l` = lane & 7.
+// ---- K-quants.  A warp task is a tile of 8 consecutive rows.  Lane (g = lane>>2, t = lane&3) owns row g of the tile and plays
+// AVX lanes l = t and l = t+4 of the reference kernel for ALL blocks of that row, in order.  Per block it fetches the two
+// 16-byte pieces of the lane-major qs plane that hold words l (the 4 lanes of a row read its 128-byte block as two full
+// 64-byte segments), computes what int32 lanes l hold in the AVX2 kernel — sumi(b,l) = Σ_sub-blocks scale · dp4a(4 weights,
+// 4 activations), the scales applied two at a time with dp2a on int16 pairs — and folds (float)sumi into its private fp32
+// accumulator with one fmaf per block.  No shared-memory staging of weights, no synchronisation; the fold order is the
+// reference's by construction, and hsum_float_8 starts in-lane (a[t] + a[t+4]) and ends with two shuffles.
+__device__ __forceinline__ int pack16(int lo, int hi) { return (int)__byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
 
-__device__ __forceinline__ float dot_q4k(const DevMat& w, int row, const ActView& a, int l) {
-  const int nb = w.nb;
-  const uint8_t* qrow = w.qs + (size_t)row * nb * 128 + l * 16;
-  const uint8_t* hrow = w.sc + (size_t)row * nb * 16;
-  float acc = 0.f, acc_m = 0.f;
-#pragma unroll 4
-  for (int b = 0; b < nb; b++) {
-    const int4 q = ldg_stream16(qrow + (size_t)b * 128);
-    const int4 h = __ldg((const int4*)(hrow + (size_t)b * 16));
-    const int4 a0 = *(const int4*)(a.qs + ((b * 2 + 0) * 8 + l) * 16);
-    const int4 a1 = *(const int4*)(a.qs + ((b * 2 + 1) * 8 + l) * 16);
-    const float yd = a.d[b];
-    uint32_t sc03, sc47, m03, m47;
-    unpack_k4((uint32_t)h.y, (uint32_t)h.z, (uint32_t)h.w, sc03, sc47, m03, m47);
-    int sumi;
-    sumi = CTB_BYTE(sc03, 0) * __dp4a((int)((uint32_t)q.x & 0x0f0f0f0fu), a0.x, 0);
-    sumi += CTB_BYTE(sc03, 1) * __dp4a((int)(((uint32_t)q.x >> 4) & 0x0f0f0f0fu), a0.y, 0);
-    sumi += CTB_BYTE(sc03, 2) * __dp4a((int)((uint32_t)q.y & 0x0f0f0f0fu), a0.z, 0);
-    sumi += CTB_BYTE(sc03, 3) * __dp4a((int)(((uint32_t)q.y >> 4) & 0x0f0f0f0fu), a0.w, 0);
-    sumi += CTB_BYTE(sc47, 0) * __dp4a((int)((uint32_t)q.z & 0x0f0f0f0fu), a1.x, 0);
-    sumi += CTB_BYTE(sc47, 1) * __dp4a((int)(((uint32_t)q.z >> 4) & 0x0f0f0f0fu), a1.y, 0);
-    sumi += CTB_BYTE(sc47, 2) * __dp4a((int)((uint32_t)q.w & 0x0f0f0f0fu), a1.z, 0);
-    sumi += CTB_BYTE(sc47, 3) * __dp4a((int)(((uint32_t)q.w >> 4) & 0x0f0f0f0fu), a1.w, 0);
-    const float dw = h2f((uint16_t)((uint32_t)h.x & 0xffffu));
-    const float dm = h2f((uint16_t)((uint32_t)h.x >> 16));
-    acc = __fmaf_rn(__fmul_rn(yd, dw), (float)sumi, acc);
-    if (l < 4) {   // mins: lane k of acc_m gets m[2k]*(bsums[4k]+bsums[4k+1]) + m[2k+1]*(bsums[4k+2]+bsums[4k+3])
-      const int2 bsv = *(const int2*)(a.bs + b * 16 + 4 * l);
-      const int s0 = (int)(short)(bsv.x & 0xffff) + (int)(short)((uint32_t)bsv.x >> 16);
-      const int s1 = (int)(short)(bsv.y & 0xffff) + (int)(short)((uint32_t)bsv.y >> 16);
-      const uint32_t mw = l < 2 ? m03 : m47;
-      const int k2 = (l & 1) * 2;
-      const int prod = CTB_BYTE(mw, k2) * s0 + CTB_BYTE(mw, k2 + 1) * s1;
-      acc_m = __fmaf_rn(__fmul_rn(-yd, dm), (float)prod, acc_m);
-    }
-  }
-  const float hs = group_hsum8(acc);
-  const float ms = group_hsum4(acc_m);   // meaningful in lanes l < 4; lane 0 of the group stores
-  return __fadd_rn(hs, ms);
+// Σ_s scale_s · dp_s for the 8 sub-block partial dots of one AVX lane; sc03 / sc47 hold the 8 scale bytes
+__device__ __forceinline__ int scale_fold(const int (&dp)[8], uint32_t sc03, uint32_t sc47) {
+  int s = __dp2a_lo(pack16(dp[0], dp[1]), (int)sc03, 0);
+  s = __dp2a_hi(pack16(dp[2], dp[3]), (int)sc03, s);
+  s = __dp2a_lo(pack16(dp[4], dp[5]), (int)sc47, s);
+  s = __dp2a_hi(pack16(dp[6], dp[7]), (int)sc47, s);
+  return s;
 }
 
-__device__ __forceinline__ float dot_q5k(const DevMat& w, int row, const ActView& a, int l) {
-  const int nb = w.nb;
-  const uint8_t* qrow = w.qs + (size_t)row * nb * 128 + l * 16;
-  const uint8_t* hrow = w.sc + (size_t)row * nb * 16;
-  const uint8_t* brow = w.qh + (size_t)row * nb * 32 + l * 4;
-  float acc = 0.f, summs = 0.f;
-#pragma unroll 4
-  for (int b = 0; b < nb; b++) {
-    const int4 q = ldg_stream16(qrow + (size_t)b * 128);
-    const int4 h = __ldg((const int4*)(hrow + (size_t)b * 16));
-    const uint32_t hb = (uint32_t)__ldg((const int*)(brow + (size_t)b * 32));   // bit s of byte e: 5th bit of element 4l+e in sub-block s
-    const int4 a0 = *(const int4*)(a.qs + ((b * 2 + 0) * 8 + l) * 16);
-    const int4 a1 = *(const int4*)(a.qs + ((b * 2 + 1) * 8 + l) * 16);
-    const float yd = a.d[b];
-    uint32_t sc03, sc47, m03, m47;
-    unpack_k4((uint32_t)h.y, (uint32_t)h.z, (uint32_t)h.w, sc03, sc47, m03, m47);
+struct ActBlock { int4 a[2][2]; float yd; };   // a[e][h]: activation words of AVX lane (e ? t+4 : t), sub-blocks 4h..4h+3
+__device__ __forceinline__ ActBlock load_act_block(const ActView& a, int b, int t) {
+  ActBlock r;
+  const int8_t* base = a.qs + (size_t)b * 256;
+  r.a[0][0] = *(const int4*)(base + t * 16);
+  r.a[1][0] = *(const int4*)(base + (t + 4) * 16);
+  r.a[0][1] = *(const int4*)(base + 128 + t * 16);
+  r.a[1][1] = *(const int4*)(base + 128 + (t + 4) * 16);
+  r.yd = a.d[b];
+  return r;
+}
+
+// What one block contributes to one row, for this lane's two AVX lanes: p0/p1 = (float)sumi of lanes t / t+4, dd = y.d·d,
+// and the mins term pm·ddm (Q4_K: mins lane k = t; Q5_K: the scalar term, lane t == 0; Q6_K: none).
+struct BlockTerms { float p0, p1, dd, pm, ddm; };
+
+// Raw block data of one lane (kept in registers by the software pipeline below)
+struct RawQ4K { int4 c0, c1, ch; };
+struct RawQ5K { int4 c0, c1, ch; uint32_t hb0, hb1; };
+struct RawQ6K { int4 ql0, ql1, scv; int2 qh0, qh1; uint16_t d; };
+__device__ __forceinline__ void load_raw(RawQ4K& r, const DevMat& w, size_t blk, int t) {
+  r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
+  r.ch = __ldg((const int4*)(w.sc + blk * 16));
+}
+__device__ __forceinline__ void load_raw(RawQ5K& r, const DevMat& w, size_t blk, int t) {
+  r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
+  r.ch = __ldg((const int4*)(w.sc + blk * 16));
+  r.hb0 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + t * 4)); r.hb1 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + 16 + t * 4));
+}
+__device__ __forceinline__ void load_raw(RawQ6K& r, const DevMat& w, size_t blk, int t) {
+  r.ql0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.ql1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
+  r.qh0 = ldg_stream8(w.qh + blk * 64 + t * 8); r.qh1 = ldg_stream8(w.qh + blk * 64 + 32 + t * 8);
+  r.scv = __ldg((const int4*)(w.sc + blk * 16));
+  r.d = __ldg(w.d + blk);
+}
+
+// k_quants.c:2651-2714
+__device__ __forceinline__ BlockTerms block_terms(const RawQ4K& raw, int b, const ActView& a, int t) {
+  const int4 c0 = raw.c0, c1 = raw.c1, ch = raw.ch;
+  const ActBlock ab = load_act_block(a, b, t);
+  uint32_t sc03, sc47, m03, m47;
+  unpack_k4((uint32_t)ch.y, (uint32_t)ch.z, (uint32_t)ch.w, sc03, sc47, m03, m47);
+  float pv[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int4 q = e ? c1 : c0;
     const uint32_t qv[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-    const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    int sumi = 0;
+    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
+    int dp[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const uint32_t lo = (qv[j] & 0x0f0f0f0fu) | (((hb >> (2 * j)) & 0x01010101u) << 4);
-      const uint32_t hi = ((qv[j] >> 4) & 0x0f0f0f0fu) | (((hb >> (2 * j + 1)) & 0x01010101u) << 4);
-      const uint32_t scw = j < 2 ? sc03 : sc47;
-      sumi += CTB_BYTE(scw, (2 * j) & 3) * __dp4a((int)lo, av[2 * j], 0);
-      sumi += CTB_BYTE(scw, (2 * j + 1) & 3) * __dp4a((int)hi, av[2 * j + 1], 0);
+      dp[2 * j] = __dp4a((int)(qv[j] & 0x0f0f0f0fu), av[2 * j], 0);
+      dp[2 * j + 1] = __dp4a((int)((qv[j] >> 4) & 0x0f0f0f0fu), av[2 * j + 1], 0);
     }
-    const float dw = h2f((uint16_t)((uint32_t)h.x & 0xffffu));
-    const float dm = h2f((uint16_t)((uint32_t)h.x >> 16));
-    acc = __fmaf_rn(__fmul_rn(yd, dw), (float)sumi, acc);
-    if (l == 0) {   // scalar mins chain of the AVX2 kernel: summs = fma(dmin, hsum, summs) (fused in the reference binary)
-      int hsum = 0;
-#pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const int s = (int)a.bs[b * 16 + 2 * k] + (int)a.bs[b * 16 + 2 * k + 1];
-        hsum += CTB_BYTE(k < 4 ? m03 : m47, k & 3) * s;
-      }
-      summs = __fmaf_rn(__fmul_rn(-yd, dm), (float)hsum, summs);
-    }
+    pv[e] = (float)scale_fold(dp, sc03, sc47);
   }
-  return __fadd_rn(group_hsum8(acc), summs);   // lane 0 of the group holds summs and stores
+  BlockTerms r;
+  r.p0 = pv[0]; r.p1 = pv[1];
+  r.dd = __fmul_rn(ab.yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
+  // mins lane k = t: m[2k]*(bsums[4k]+bsums[4k+1]) + m[2k+1]*(bsums[4k+2]+bsums[4k+3])
+  const int2 bsv = *(const int2*)(a.bs + b * 16 + 4 * t);
+  const int s0 = (int)(short)(bsv.x & 0xffff) + (int)(short)((uint32_t)bsv.x >> 16);
+  const int s1 = (int)(short)(bsv.y & 0xffff) + (int)(short)((uint32_t)bsv.y >> 16);
+  const uint32_t mw = (t < 2 ? m03 : m47) >> ((t & 1) * 16);
+  r.pm = (float)((int)(mw & 0xffu) * s0 + (int)((mw >> 8) & 0xffu) * s1);
+  r.ddm = __fmul_rn(-ab.yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
+  return r;
 }
 
-__device__ __forceinline__ float dot_q6k(const DevMat& w, int row, const ActView& a, int l) {
-  const int nb = w.nb;
-  const uint8_t* lrow = w.qs + (size_t)row * nb * 128 + l * 16;
-  const uint8_t* hrow = w.qh + (size_t)row * nb * 64 + l * 8;
-  const uint8_t* srow = w.sc + (size_t)row * nb * 16;
-  const uint16_t* drow = w.d + (size_t)row * nb;
-  const int hi16 = l >> 2;   // elements 0..15 of a 32-group use the even scale, 16..31 the odd one
-  float acc = 0.f;
-#pragma unroll 4
-  for (int b = 0; b < nb; b++) {
-    const int4 ql = ldg_stream16(lrow + (size_t)b * 128);     // words: (jj=0,v=0) (0,1) (1,0) (1,1)
-    const int2 qh = ldg_stream8(hrow + (size_t)b * 64);       // words: jj=0, jj=1
-    const int4 scv = __ldg((const int4*)(srow + (size_t)b * 16));
-    const float dw = h2f(__ldg(drow + b));
-    const int4 a0 = *(const int4*)(a.qs + ((b * 2 + 0) * 8 + l) * 16);
-    const int4 a1 = *(const int4*)(a.qs + ((b * 2 + 1) * 8 + l) * 16);
-    const float yd = a.d[b];
+// k_quants.c:3174-3262
+__device__ __forceinline__ BlockTerms block_terms(const RawQ5K& raw, int b, const ActView& a, int t) {
+  const int4 c0 = raw.c0, c1 = raw.c1, ch = raw.ch;
+  const uint32_t hb[2] = {raw.hb0, raw.hb1};
+  const ActBlock ab = load_act_block(a, b, t);
+  uint32_t sc03, sc47, m03, m47;
+  unpack_k4((uint32_t)ch.y, (uint32_t)ch.z, (uint32_t)ch.w, sc03, sc47, m03, m47);
+  float pv[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const int4 q = e ? c1 : c0;
+    const uint32_t qv[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
+    int dp[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {   // bit s of a qh byte: 5th bit of the element in sub-block s
+      const uint32_t lo = (qv[j] & 0x0f0f0f0fu) | (((hb[e] >> (2 * j)) & 0x01010101u) << 4);
+      const uint32_t hi = ((qv[j] >> 4) & 0x0f0f0f0fu) | (((hb[e] >> (2 * j + 1)) & 0x01010101u) << 4);
+      dp[2 * j] = __dp4a((int)lo, av[2 * j], 0);
+      dp[2 * j + 1] = __dp4a((int)hi, av[2 * j + 1], 0);
+    }
+    pv[e] = (float)scale_fold(dp, sc03, sc47);
+  }
+  BlockTerms r;
+  r.p0 = pv[0]; r.p1 = pv[1];
+  r.dd = __fmul_rn(ab.yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
+  int hsum = 0;   // scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]) — used by lane t == 0 only
+  if (t == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) hsum += CTB_BYTE(k < 4 ? m03 : m47, k & 3) * ((int)a.bs[b * 16 + 2 * k] + (int)a.bs[b * 16 + 2 * k + 1]);
+  }
+  r.pm = (float)hsum;
+  r.ddm = __fmul_rn(-ab.yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
+  return r;
+}
+
+// k_quants.c:3794-3872
+__device__ __forceinline__ BlockTerms block_terms(const RawQ6K& raw, int b, const ActView& a, int t) {
+  const int4 ql0 = raw.ql0, ql1 = raw.ql1, scv = raw.scv;
+  const int2 qh0 = raw.qh0, qh1 = raw.qh1;
+  const float dw = h2f(raw.d);
+  const ActBlock ab = load_act_block(a, b, t);
+  const uint32_t scw[4] = {(uint32_t)scv.x, (uint32_t)scv.y, (uint32_t)scv.z, (uint32_t)scv.w};
+  float pv[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {   // e = 0: AVX lane t (elements 0..15 of each 32-group, even scales); e = 1: lane t+4 (odd scales)
+    const int4 ql = e ? ql1 : ql0;   // words: (jj=0,v=0) (0,1) (1,0) (1,1)
+    const int2 qh = e ? qh1 : qh0;   // words: jj=0, jj=1
     const uint32_t A[2] = {(uint32_t)ql.x, (uint32_t)ql.z}, B[2] = {(uint32_t)ql.y, (uint32_t)ql.w}, H[2] = {(uint32_t)qh.x, (uint32_t)qh.y};
-    const int av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const uint32_t scw[4] = {(uint32_t)scv.x, (uint32_t)scv.y, (uint32_t)scv.z, (uint32_t)scv.w};
+    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
     int sumi = 0;
 #pragma unroll
     for (int jj = 0; jj < 2; jj++) {
-      const uint32_t u0 = (A[jj] & 0x0f0f0f0fu) | ((H[jj] << 4) & 0x30303030u);
-      const uint32_t u1 = (B[jj] & 0x0f0f0f0fu) | ((H[jj] << 2) & 0x30303030u);
-      const uint32_t u2 = ((A[jj] >> 4) & 0x0f0f0f0fu) | (H[jj] & 0x30303030u);
-      const uint32_t u3 = ((B[jj] >> 4) & 0x0f0f0f0fu) | ((H[jj] >> 2) & 0x30303030u);
-      const uint32_t uu[4] = {u0, u1, u2, u3};
+      const uint32_t uu[4] = {(A[jj] & 0x0f0f0f0fu) | ((H[jj] << 4) & 0x30303030u), (B[jj] & 0x0f0f0f0fu) | ((H[jj] << 2) & 0x30303030u),
+                              ((A[jj] >> 4) & 0x0f0f0f0fu) | (H[jj] & 0x30303030u), ((B[jj] >> 4) & 0x0f0f0f0fu) | ((H[jj] >> 2) & 0x30303030u)};
 #pragma unroll
       for (int m = 0; m < 4; m++) {
         const int aw = av[jj * 4 + m];
-        // (q6 - 32)·q8 over 4 elements = u·q8 - 32·Σq8   (the AVX2 kernel does the same with maddubs(m32s, q8))
-        const int s = __dp4a((int)uu[m], aw, 0) - 32 * __dp4a(0x01010101, aw, 0);
-        const int sidx = 8 * jj + 2 * m + hi16;   // int8 scale of this 16-element sub-block
+        const int sidx = 8 * jj + 2 * m + e;   // int8 scale of this 16-element sub-block
         const int scale = (int)(int8_t)CTB_BYTE(scw[sidx >> 2], sidx & 3);
-        sumi += scale * s;
+        // (q6 - 32)·q8 = u·q8 - 32·Σq8, as the AVX2 kernel does with maddubs(m32s, q8)
+        sumi += scale * (__dp4a((int)uu[m], aw, 0) - 32 * __dp4a(0x01010101, aw, 0));
       }
     }
-    acc = __fmaf_rn(__fmul_rn(yd, dw), (float)sumi, acc);
+    pv[e] = (float)sumi;
   }
-  return group_hsum8(acc);
+  BlockTerms r;
+  r.p0 = pv[0]; r.p1 = pv[1]; r.dd = __fmul_rn(ab.yd, dw); r.pm = 0.f; r.ddm = 0.f;
+  return r;
+}
+
+// running state of one row's fold in this lane
+struct Fold { float a0, a1, am; };
+__device__ __forceinline__ void fold_block(Fold& f, const BlockTerms& x) {
+  f.a0 = __fmaf_rn(x.dd, x.p0, f.a0);
+  f.a1 = __fmaf_rn(x.dd, x.p1, f.a1);
+  f.am = __fmaf_rn(x.ddm, x.pm, f.am);
+}
+// hsum_float_8 (ggml.c:609-615) + the mins tail; finished row value in every lane of the row's 4-lane group
+__device__ __forceinline__ float fold_finish(int type, const Fold& f) {
+  float r = __fadd_rn(f.a1, f.a0);                        // res[l] = x[l+4] + x[l]
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // res[0]+res[2], res[1]+res[3]
+  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  float m = f.am;
+  if (type == GT_Q4_K) {                                  // acc_m: (m0+m2) + (m1+m3)
+    m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  } else if (type == GT_Q5_K) {
+    m = __shfl_sync(0xffffffffu, m, 0, 4);                // the scalar mins chain lives in lane t == 0
+  } else {
+    return r;
+  }
+  return __fadd_rn(r, m);
+}
+
+// Row `row` of a K-quant matrix, blocks [b0, b1).  split == 1: the whole row, folded as the blocks are computed.
+// split > 1 (K-split): `slice` of `split` consecutive warps share the row tile; this warp parks its blocks' terms in its
+// private buffer, waits for the fold state of the previous slice (shared-memory mailbox + flag), folds its blocks in order
+// and hands the state on; the last slice finishes.  The fold order is identical to the unsplit one.
+struct SplitCtx {
+  int split, slice, wave;        // wave: monotonically increasing id of this hand-off round
+  float* buf;                    // warp-private [nbs][5][32] floats
+  volatile float* mail;          // [3][32] floats of the chain this warp hands to (indexed by the RECEIVING slice)
+  volatile float* mail_in;       // mailbox this warp receives from
+  volatile int* flag_out;        // set to wave+1 when mail is valid
+  volatile int* flag_in;
+};
+
+// Blocks [b0, b1) of one row through a D-deep register pipeline: the loads of block b+D are issued before block b is
+// computed, so every lane keeps D blocks (D x 48..68 bytes) in flight.  sink(b, terms) is called in block order.
+template <typename Raw, int D, typename Sink>
+__device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0, int b1, const ActView& a, int t, Sink sink) {
+  if (b0 >= b1) return;
+  Raw ring[D];
+  const int last = b1 - 1;
+#pragma unroll
+  for (int i = 0; i < D; i++) load_raw(ring[i], w, rb + min(b0 + i, last), t);   // tail slots re-load the last block (a cache hit)
+  for (int b = b0; b < b1; b += D) {
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+      const Raw cur = ring[i];
+      load_raw(ring[i], w, rb + min(b + i + D, last), t);
+      if (b + i < b1) sink(b + i, block_terms(cur, b + i, a, t));
+    }
+  }
+}
+
+template <typename Raw, int D>
+__device__ __forceinline__ bool row_kquant_typed(const DevMat& w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
+  const int t = lane & 3, nb = w.nb;
+  const size_t rb = (size_t)row * nb;
+  Fold f{0.f, 0.f, 0.f};
+  if (cx.split == 1) {
+    stream_blocks<Raw, D>(w, rb, 0, nb, a, t, [&](int, const BlockTerms& x) { fold_block(f, x); });
+    out = fold_finish(w.type, f);
+    return true;
+  }
+  const int nbs = (nb + cx.split - 1) / cx.split, b0 = cx.slice * nbs, b1 = min(nb, b0 + nbs);
+  stream_blocks<Raw, D>(w, rb, b0, b1, a, t, [&](int b, const BlockTerms& x) {
+    float* s = cx.buf + (size_t)(b - b0) * 160 + lane;
+    s[0] = x.p0; s[32] = x.p1; s[64] = x.dd; s[96] = x.pm; s[128] = x.ddm;
+  });
+  if (cx.slice > 0) {
+    while (*cx.flag_in < cx.wave + 1) { }
+    __syncwarp();
+    f.a0 = cx.mail_in[lane]; f.a1 = cx.mail_in[32 + lane]; f.am = cx.mail_in[64 + lane];
+  }
+  for (int b = b0; b < b1; b++) {
+    const float* s = cx.buf + (size_t)(b - b0) * 160 + lane;
+    BlockTerms x; x.p0 = s[0]; x.p1 = s[32]; x.dd = s[64]; x.pm = s[96]; x.ddm = s[128];
+    fold_block(f, x);
+  }
+  if (cx.slice + 1 < cx.split) {
+    cx.mail[lane] = f.a0; cx.mail[32 + lane] = f.a1; cx.mail[64 + lane] = f.am;
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *cx.flag_out = cx.wave + 1;
+    return false;
+  }
+  out = fold_finish(w.type, f);
+  return true;
+}
+
+__device__ __forceinline__ bool row_kquant_split(const DevMat& w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
+  if (w.type == GT_Q4_K) return row_kquant_typed<RawQ4K, 4>(w, row, a, lane, cx, out);
+  if (w.type == GT_Q6_K) return row_kquant_typed<RawQ6K, 3>(w, row, a, lane, cx, out);
+  return row_kquant_typed<RawQ5K, 3>(w, row, a, lane, cx, out);
 }
 
 // Q4_0: natural plane; lane l uses word (l & 3) of the block's 16 nibble bytes, low nibbles for l < 4 (elements 4l..4l+3),
@@ -433,14 +583,8 @@ __device__ __forceinline__ float dot_q80(const DevMat& w, int row, const ActView
   return group_hsum8(acc);
 }
 
-__device__ __forceinline__ float dot_quant(const DevMat& w, int row, const ActView& a, int l) {
-  switch (w.type) {
-    case GT_Q4_K: return dot_q4k(w, row, a, l);
-    case GT_Q6_K: return dot_q6k(w, row, a, l);
-    case GT_Q5_K: return dot_q5k(w, row, a, l);
-    case GT_Q4_0: return dot_q40(w, row, a, l);
-    default: return dot_q80(w, row, a, l);
-  }
+__device__ __forceinline__ float dot_legacy(const DevMat& w, int row, const ActView& a, int l) {
+  return w.type == GT_Q4_0 ? dot_q40(w, row, a, l) : dot_q80(w, row, a, l);
 }
 
 // GGML_F32x8_REDUCE over a warp that plays 4 accumulators x 8 lanes (lane = 8*j + l): (0+2),(1+3) -> (0+1) -> lo128+hi128 ->
@@ -487,50 +631,121 @@ __device__ __forceinline__ void store_epilogue(const MVSeg& sg, const MVParams& 
   sg.out[row] = v;
 }
 
-// rows one work unit (one warp-iteration) covers for a weight type
-__host__ __device__ inline int rows_per_unit(int type) { return (type == GT_F16 || type == GT_F32) ? 1 : MV_ROWS; }
+constexpr int MV_KQ_ROWS = 8;      // K-quants: rows per tile (4 lanes per row)
+constexpr int MV_SPLIT_MAXB = 12;  // K-split: most blocks one slice may own (sizes the per-warp term buffer)
+
+// rows one work unit (one warp task) covers for a weight type
+__host__ __device__ inline int rows_per_unit(int type) {
+  if (type == GT_F16 || type == GT_F32) return 1;
+  return type_is_kquant(type) ? MV_KQ_ROWS : MV_ROWS;
+}
 
 // ---------------------------------------------------------------------------------------------
-static __global__ void __launch_bounds__(MV_THREADS) k_matvec(const __grid_constant__ MVParams p) {
+// Persistent: grid = number of SMs, one CTA each.  K-quant launches: `split` consecutive warps share an 8-row tile, a CTA
+// works on MV_WARPS/split tiles per wave.  Other types: warp tasks strided over all warps of the grid.
+static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p, const int split) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
+  __shared__ float mailbox[MV_WARPS][2][96];   // [receiving warp][gate/up chain][3*32]
+  __shared__ int flags[MV_WARPS][2];
+  if (threadIdx.x < MV_WARPS * 2) ((int*)flags)[threadIdx.x] = 0;
   stage_activation(p.x, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
   const ActView a = act_view(p.act, p.K, smem);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l = lane & 7, g = lane >> 3;
-  const int gw = blockIdx.x * MV_WARPS + warp, nw = gridDim.x * MV_WARPS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool kq = type_is_kquant(p.seg[0].w.type);
 
+  if (kq) {
+    // tile space: all segments concatenated (pair mode: the gate matrix's tiles; each tile also runs the up matrix)
+    int tiles_seg[MV_MAX_SEG], ntiles = 0;
+    const int nseg = p.pair_silu ? 1 : p.nseg;
+    for (int s = 0; s < nseg; s++) { tiles_seg[s] = (p.seg[s].w.M + MV_KQ_ROWS - 1) / MV_KQ_ROWS; ntiles += tiles_seg[s]; }
+    const int tpw = MV_WARPS / split;                      // tiles per CTA wave
+    const int slice = warp % split, slot = warp / split;
+    float* buf = (float*)(smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15)) + (size_t)warp * MV_SPLIT_MAXB * 160;
+    int wave = 0;
+    for (int t0 = blockIdx.x * tpw; t0 < ntiles; t0 += gridDim.x * tpw, wave++) {
+      int tile = t0 + slot;
+      if (tile < ntiles) {                                  // uniform across the split warps of a tile
+        int s = 0;
+        while (tile >= tiles_seg[s]) { tile -= tiles_seg[s]; s++; }
+        const MVSeg& sg = p.seg[s];
+        const int row = tile * MV_KQ_ROWS + (lane >> 2), rc = min(row, sg.w.M - 1);
+        SplitCtx cx;
+        cx.split = split; cx.slice = slice; cx.wave = wave; cx.buf = buf;
+        cx.mail = mailbox[(warp + 1) % MV_WARPS][0]; cx.mail_in = mailbox[warp][0];
+        cx.flag_out = &flags[(warp + 1) % MV_WARPS][0]; cx.flag_in = &flags[warp][0];
+        float v = 0.f, vu = 0.f;
+        const bool done = row_kquant_split(sg.w, rc, a, lane, cx, v);
+        if (p.pair_silu) {
+          cx.mail = mailbox[(warp + 1) % MV_WARPS][1]; cx.mail_in = mailbox[warp][1];
+          cx.flag_out = &flags[(warp + 1) % MV_WARPS][1]; cx.flag_in = &flags[warp][1];
+          row_kquant_split(p.seg[1].w, rc, a, lane, cx, vu);
+          if (done && (lane & 3) == 0 && row < sg.w.M) sg.out[row] = __fmul_rn(table_f16(p.silu_tab, v), vu);
+        } else if (done && (lane & 3) == 0 && row < sg.w.M) {
+          store_epilogue(sg, p, row, v);
+        }
+      }
+      if (split > 1) __syncthreads();   // nobody starts the next hand-off round before every mailbox of this one has been read
+    }
+    return;
+  }
+
+  const int gw = blockIdx.x * MV_WARPS + warp, nw = gridDim.x * MV_WARPS;
   if (p.pair_silu) {
     const DevMat& gm = p.seg[0].w;
     const DevMat& um = p.seg[1].w;
     const int units = (gm.M + MV_ROWS - 1) / MV_ROWS;
     for (int un = gw; un < units; un += nw) {
-      const int row = un * MV_ROWS + g, rc = min(row, gm.M - 1);
-      const float vg = dot_quant(gm, rc, a, l);
-      const float vu = dot_quant(um, rc, a, l);
-      if (l == 0 && row < gm.M) p.seg[0].out[row] = __fmul_rn(table_f16(p.silu_tab, vg), vu);
+      const int row = un * MV_ROWS + (lane >> 3), rc = min(row, gm.M - 1);
+      const float vg = dot_legacy(gm, rc, a, lane & 7), vu = dot_legacy(um, rc, a, lane & 7);
+      if ((lane & 7) == 0 && row < gm.M) p.seg[0].out[row] = __fmul_rn(table_f16(p.silu_tab, vg), vu);
     }
     return;
   }
-
-  int unit_base = 0;
+  int first = gw;   // global striding continues across segments so all warps stay busy
   for (int s = 0; s < p.nseg; s++) {
     const MVSeg& sg = p.seg[s];
-    const int rpu = rows_per_unit(sg.w.type);
+    const int type = sg.w.type;
+    const int rpu = rows_per_unit(type);
     const int units = (sg.w.M + rpu - 1) / rpu;
-    int first = gw - (unit_base % nw);   // continue the global striding across segments so all warps stay busy
-    if (first < 0) first += nw;
-    for (int un = first; un < units; un += nw) {
+    int un = first;
+    for (; un < units; un += nw) {
       if (rpu == 1) {
-        const float v = sg.w.type == GT_F16 ? dot_f16_row(sg.w, un, smem, lane) : dot_f32_row(sg.w, un, smem, lane);
+        const float v = type == GT_F16 ? dot_f16_row(sg.w, un, smem, lane) : dot_f32_row(sg.w, un, smem, lane);
         if (lane == 0) store_epilogue(sg, p, un, v);
       } else {
-        const int row = un * MV_ROWS + g;
-        const float v = dot_quant(sg.w, min(row, sg.w.M - 1), a, l);
-        if (l == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
+        const int row = un * MV_ROWS + (lane >> 3);
+        const float v = dot_legacy(sg.w, min(row, sg.w.M - 1), a, lane & 7);
+        if ((lane & 7) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
       }
     }
-    unit_base += units;
+    first = un - units;   // where this warp lands in the next segment
   }
+}
+
+// host-side launch geometry shared by the engine and the op-level entry points
+struct MVLaunch { int split; int grid; size_t smem; };
+inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
+  MVLaunch L;
+  const size_t act = (act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15;
+  const int nseg = p.pair_silu ? 1 : p.nseg;
+  const bool kq = type_is_kquant(p.seg[0].w.type);
+  long units = 0;
+  for (int s = 0; s < nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
+  L.split = 1;
+  if (kq) {
+    const int nb = p.K / 256;
+    const long warps = (long)n_sm * MV_WARPS;
+    while (L.split < 8 && units * L.split * 4 < warps * 3 && nb / (L.split * 2) >= 2) L.split *= 2;   // give ~every warp a task
+    while (L.split < 8 && (nb + L.split - 1) / L.split > MV_SPLIT_MAXB && L.split > 1) L.split *= 2;
+    const int tpw = MV_WARPS / L.split;
+    L.grid = (int)std::max<long>(1, std::min<long>((units + tpw - 1) / tpw, (long)n_sm));
+    L.smem = act + (L.split > 1 ? (size_t)MV_WARPS * MV_SPLIT_MAXB * 160 * 4 : 0);
+  } else {
+    L.grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)n_sm));
+    L.smem = act;
+  }
+  return L;
 }
 
 }  // namespace ctb

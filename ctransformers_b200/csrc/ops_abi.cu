@@ -88,21 +88,18 @@ void upload(OwnedMat& o, int type, const void* blocks, int K, int M) {
   o.m.qs = (const uint8_t*)pl[0]; o.m.qh = (const uint8_t*)pl[1]; o.m.sc = (const uint8_t*)pl[2]; o.m.d = pl[3];
 }
 
-long matvec_units(const MVParams& p) {
-  if (p.pair_silu) return (p.seg[0].w.M + MV_ROWS - 1) / MV_ROWS;
-  long units = 0;
-  for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
-  return units;
-}
-
 void run_matvec(MVParams& p) {
   p.silu_tab = tables().silu;
   p.gelu_tab = tables().gelu;
-  const long units = matvec_units(p);
-  const int grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, 148L * 8));
-  const size_t smem = act_smem_bytes(p.act, p.K);
-  if (smem > 48 * 1024) OPS_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_matvec<<<grid, MV_THREADS, smem>>>(p);
+  static bool attr = false;
+  if (!attr) {
+    OPS_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+  const MVLaunch L = matvec_launch_shape(p, n_sm);
+  k_matvec<<<L.grid, MV_THREADS, L.smem, 0>>>(p, L.split);
   OPS_CUDA(cudaGetLastError());
 }
 
@@ -247,18 +244,32 @@ int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache
           kp[((size_t)t * n_kv + kh) * head_dim + k_perm(e, head_dim)] = kcache[((size_t)t * n_kv + kh) * head_dim + e];
     for (int ch = 0; ch < n_kv * head_dim; ch++)
       for (int t = 0; t < T; t++) vp[(size_t)ch * cp + v_perm(t)] = vcache[(size_t)ch * T + t];
-    DevBuf dq(nq * 4), dk(kp.size() * 2), dv(vp.size() * 2), dout(nq * 4), dst(16);
+    // the kernel fuses RoPE + KV store for the current position: feed it an identity rotation (cos 1, sin 0 is exact) and the
+    // current position's k/v taken back out of the caller's caches (f16 -> f32 -> f16 round-trips exactly)
+    const int pos = T - 1;
+    std::vector<float> kcur((size_t)n_kv * head_dim), vcur((size_t)n_kv * head_dim);
+    for (int kh = 0; kh < n_kv; kh++)
+      for (int e = 0; e < head_dim; e++) {
+        kcur[(size_t)kh * head_dim + e] = __half2float(__ushort_as_half(kcache[((size_t)pos * n_kv + kh) * head_dim + e]));
+        vcur[(size_t)kh * head_dim + e] = __half2float(__ushort_as_half(vcache[((size_t)kh * head_dim + e) * T + pos]));
+      }
+    std::vector<float2> ident((size_t)n_total * (head_dim / 2), make_float2(1.f, 0.f));
+    DevBuf dq(nq * 4), dk(kp.size() * 2), dv(vp.size() * 2), dout(nq * 4), dst(16), dkc(kcur.size() * 4), dvc(vcur.size() * 4), dtab(ident.size() * 8);
     OPS_CUDA(cudaMemcpy(dq.p, q, nq * 4, cudaMemcpyHostToDevice));
     OPS_CUDA(cudaMemcpy(dk.p, kp.data(), kp.size() * 2, cudaMemcpyHostToDevice));
     OPS_CUDA(cudaMemcpy(dv.p, vp.data(), vp.size() * 2, cudaMemcpyHostToDevice));
-    const int st[4] = {0, T - 1, 0, n_total};
+    OPS_CUDA(cudaMemcpy(dkc.p, kcur.data(), kcur.size() * 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dvc.p, vcur.data(), vcur.size() * 4, cudaMemcpyHostToDevice));
+    OPS_CUDA(cudaMemcpy(dtab.p, ident.data(), ident.size() * 8, cudaMemcpyHostToDevice));
+    const int st[4] = {0, pos, 0, n_total};
     OPS_CUDA(cudaMemcpy(dst.p, st, 16, cudaMemcpyHostToDevice));
     AttnParams ap{};
-    ap.q = dq.as<float>(); ap.kc = dk.as<uint16_t>(); ap.vc = dv.as<uint16_t>(); ap.out = dout.as<float>(); ap.exp_tab = tables().ex;
-    ap.state = dst.as<int>(); ap.kq_scale = kq_scale; ap.n_head = n_head; ap.n_kv = n_kv; ap.hd = head_dim; ap.n_ctx = n_total; ap.q_stride = (int)nq;
+    ap.q = dq.as<float>(); ap.k = dkc.as<float>(); ap.v = dvc.as<float>(); ap.kc = dk.as<uint16_t>(); ap.vc = dv.as<uint16_t>();
+    ap.out = dout.as<float>(); ap.exp_tab = tables().ex; ap.rope = dtab.as<float2>(); ap.state = dst.as<int>(); ap.kq_scale = kq_scale;
+    ap.n_head = n_head; ap.n_kv = n_kv; ap.hd = head_dim; ap.n_ctx = n_total; ap.q_stride = (int)nq; ap.kv_stride = n_kv * head_dim; ap.neox = 0;
     const size_t smem = attn_smem_bytes(n_total, head_dim);
     OPS_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    k_attn<<<dim3(n_head, 1), ATTN_THREADS, smem>>>(ap);
+    k_attn<<<dim3(n_head, 1, head_dim / ATTN_CH), ATTN_THREADS, smem>>>(ap);
     OPS_CUDA(cudaGetLastError());
     OPS_CUDA(cudaMemcpy(out, dout.p, nq * 4, cudaMemcpyDeviceToHost));
   });
