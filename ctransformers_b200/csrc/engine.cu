@@ -53,7 +53,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += 3 * align_up(65536 * 2, 256);
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
-  total += 4 * (2 * (size_t)hp.n_embd + qkv + 3 * (size_t)hp.n_embd + (size_t)hp.n_ff + (size_t)hp.n_vocab) + 64 * 256;
+  total += 4 * (2 * (size_t)hp.n_embd + qkv + 3 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + (size_t)hp.n_vocab) + 64 * 256;
   total += 1 << 20;
   return total;
 }
@@ -230,6 +230,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   qkv_ = (float*)alloc(qkv * 4);
   attn_ = (float*)alloc(hp_.n_embd * 4); attn_o_ = (float*)alloc(hp_.n_embd * 4);
   ffn_ = (float*)alloc((size_t)hp_.n_ff * 4);
+  ffn2_ = (float*)alloc((size_t)hp_.n_ff * 4);
   d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
   d_embd_ = (float*)alloc(hp_.n_embd * 4);
   CTB_CUDA(cudaMemset(d_state_, 0, 64));
@@ -238,7 +239,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
-  CTB_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CTB_CUDA(matvec_set_smem_limit(200 * 1024));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();
@@ -269,7 +270,7 @@ void Engine::launch_matvec(MVParams& p) {
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
   const MVLaunch L = matvec_launch_shape(p, sm_count_);
-  k_matvec<<<L.grid, MV_THREADS, L.smem, stream_>>>(p, L.split);
+  launch_matvec_kernel(L, stream_, p);
   launches_per_step_++;
   mark(0);
 }
@@ -325,16 +326,16 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.seg[0] = seg(L.wo, y, EPI_ADD, x);
         launch_matvec(p);
       }
-      {  // ffn_norm + silu(w1 x) * (w3 x)
+      {  // ffn_norm + gate and up projections as two independent row sets (SiLU·mul is applied by the consumer's prologue)
         MVParams p{};
         p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
-        p.act = act_format_for(L.w1.type); p.nseg = 2; p.pair_silu = 1;
-        p.seg[0] = seg(L.w1, ffn_); p.seg[1] = seg(L.w3, nullptr);
+        p.act = act_format_for(L.w1.type); p.nseg = 2;
+        p.seg[0] = seg(L.w1, ffn_); p.seg[1] = seg(L.w3, ffn2_);
         launch_matvec(p);
       }
-      {  // w2 + residual
+      {  // w2 on silu(gate)*up, + residual
         MVParams p{};
-        p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.x = ffn_; p.x2 = ffn2_; p.x_mode = 1; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, x, EPI_ADD, y);
         launch_matvec(p);
       }
@@ -350,14 +351,14 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.norm_w = two_norms ? L.attn_norm2 : L.attn_norm; p.norm_b = two_norms ? L.attn_norm2_b : L.attn_norm_b;
         p.act = act_format_for(L.wqkv.type); p.nseg = 1;
         p.seg[0] = seg(L.wqkv, qkv_);
-        if (fuse) { p.seg[1] = seg(L.w3, ffn_, EPI_GELU); p.nseg = 2; }
+        if (fuse) { p.seg[1] = seg(L.w3, ffn_); p.nseg = 2; }   // GELU is applied by ffn_down's prologue
         launch_matvec(p);
       }
       if (!fuse) {
         MVParams p{};
         p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd; p.norm_w = L.attn_norm; p.norm_b = L.attn_norm_b;
         p.act = act_format_for(L.w3.type); p.nseg = 1;
-        p.seg[0] = seg(L.w3, ffn_, EPI_GELU);
+        p.seg[0] = seg(L.w3, ffn_);
         launch_matvec(p);
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
@@ -372,7 +373,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
       }
       {  // ffn_down, then + attn_out, then + layer input (llama.cpp:2767-2771 order)
         MVParams p{};
-        p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.x = ffn_; p.x_mode = 2; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, y, EPI_ADD2, attn_o_, x);
         launch_matvec(p);
       }

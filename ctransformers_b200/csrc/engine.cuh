@@ -79,7 +79,7 @@ class Engine {
   uint16_t *kc_ = nullptr, *vc_ = nullptr;
   // workspace
   int* d_state_ = nullptr;     // {token, n_past}
-  float *xa_ = nullptr, *xb_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *attn_o_ = nullptr, *ffn_ = nullptr, *d_logits_ = nullptr, *d_embd_ = nullptr;
+  float *xa_ = nullptr, *xb_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *attn_o_ = nullptr, *ffn_ = nullptr, *ffn2_ = nullptr, *d_logits_ = nullptr, *d_embd_ = nullptr;
   // host (pinned) results
   float *h_logits_ = nullptr, *h_embd_ = nullptr;
   int* h_state_ = nullptr;     // pinned ring of {token, n_past}

@@ -42,6 +42,8 @@ struct MVSeg {
 
 struct MVParams {
   const float* x;        // [K] f32 input
+  const float* x2;       // x_mode 1: second operand
+  int x_mode;            // 0: x;  1: silu_table(x) * x2 (ggml_silu + ggml_mul, llama.cpp:2438-2443);  2: gelu_table(x) (falcon)
   const float* norm_w;   // [K] or null
   const float* norm_b;   // [K] or null (LayerNorm bias)
   float* norm_out;       // optional [K]: CTA 0 writes the normalised vector (result_norm / embeddings)
@@ -123,14 +125,32 @@ __device__ __forceinline__ uint32_t pack4(const int* q) {
   return (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
 }
 
-__device__ __forceinline__ void stage_activation(const float* x, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
+// 16 consecutive input elements with the producer's activation applied: the reference's fp16-table SiLU (ggml.c:3625-3632)
+// times the up projection, or the fp16-table GELU (ggml.c:3568-3575) — fused here instead of in the producing kernel so that
+// gate and up can be two independent row sets there.
+__device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid, float (&v)[16]) {
+  load16(xs.x + base, valid, v);
+  if (xs.x_mode == 1) {
+    float u[16];
+    load16(xs.x2 + base, valid, u);
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = __fmul_rn(h2f(__ldg(xs.silu_tab + f2h(v[e]))), u[e]);
+  } else if (xs.x_mode == 2) {
+#pragma unroll
+    for (int e = 0; e < 16; e++) v[e] = h2f(__ldg(xs.gelu_tab + f2h(v[e])));
+  }
+}
+
+__device__ __forceinline__ void stage_activation(const MVParams& xs, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
                                                   int K, int act, uint8_t* smem, double* red, bool write_norm) {
   const int t = threadIdx.x, lane = t & 31;
   const int passes = (K + MV_THREADS * 16 - 1) / (MV_THREADS * 16);
   // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
   float mean = 0.f, scale = 1.f;
-  float v0[16];            // pass 0's elements stay in registers: with K <= 16384 the quantize step needs no second read of x
-  load16(x + t * 16, K - t * 16, v0);
+  float v0[16], w0[16], bias0[16];   // pass 0's x / norm weight / bias stay in registers: all global loads of the prologue are
+  load16x(xs, t * 16, K - t * 16, v0);   // issued here, back to back, and their latencies overlap
+  if (norm_mode != NORM_NONE && nw) load16(nw + t * 16, K - t * 16, w0);
+  if (norm_mode != NORM_NONE && nb_) load16(nb_ + t * 16, K - t * 16, bias0);
   if (norm_mode == NORM_RMS) {
     double ss = 0.0;
     for (int ps = 0; ps < passes; ps++) {
@@ -139,7 +159,7 @@ __device__ __forceinline__ void stage_activation(const float* x, const float* nw
       if (ps == 0) {
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = v0[e];
-      } else load16(x + base, K - base, v);
+      } else load16x(xs, base, K - base, v);
 #pragma unroll
       for (int e = 0; e < 16; e++) ss += (double)__fmul_rn(v[e], v[e]);
     }
@@ -151,7 +171,7 @@ __device__ __forceinline__ void stage_activation(const float* x, const float* nw
     for (int ps = 0; ps < passes; ps++) {
       const int base = (ps * MV_THREADS + t) * 16;
       float v[16];
-      load16(x + base, K - base, v);
+      load16x(xs, base, K - base, v);
 #pragma unroll
       for (int e = 0; e < 16; e++) s1 += (double)v[e];
     }
@@ -161,7 +181,7 @@ __device__ __forceinline__ void stage_activation(const float* x, const float* nw
     for (int ps = 0; ps < passes; ps++) {
       const int base = (ps * MV_THREADS + t) * 16;
       float v[16];
-      load16(x + base, K - base, v);
+      load16x(xs, base, K - base, v);
 #pragma unroll
       for (int e = 0; e < 16; e++) { const float d = (base + e < K) ? __fsub_rn(v[e], mean) : 0.f; s2 += (double)__fmul_rn(d, d); }
     }
@@ -181,11 +201,16 @@ __device__ __forceinline__ void stage_activation(const float* x, const float* nw
     if (ps == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = v0[e];
-    } else load16(x + base, valid, v);
+    } else load16x(xs, base, valid, v);
     if (norm_mode != NORM_NONE) {
       float w[16], bb[16];
-      if (nw) load16(nw + base, valid, w);
-      if (nb_) load16(nb_ + base, valid, bb);
+      if (ps == 0) {
+#pragma unroll
+        for (int e = 0; e < 16; e++) { w[e] = w0[e]; bb[e] = bias0[e]; }
+      } else {
+        if (nw) load16(nw + base, valid, w);
+        if (nb_) load16(nb_ + base, valid, bb);
+      }
 #pragma unroll
       for (int e = 0; e < 16; e++) {
         float y = v[e];
@@ -486,6 +511,18 @@ struct SplitCtx {
   volatile int* flag_in;
 };
 
+// Ask the memory system for blocks [b0, b1) of this lane's row right away (L2 prefetch, no registers held): the 4 lanes of a
+// row take turns over its 128-byte lines.  The register pipeline below then finds its data in L2.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0, int b1, int t) {
+  for (int b = b0 + t; b < b1; b += 4) {
+    prefetch_l2(w.qs + (rb + b) * 128);
+    if (w.type == GT_Q6_K && (b & 1) == 0) prefetch_l2(w.qh + (rb + b) * 64);
+    if (w.type == GT_Q5_K && (b & 3) == t) prefetch_l2(w.qh + (rb + b) * 32);
+    if ((b & 7) == t) prefetch_l2(w.sc + (rb + b) * 16);
+  }
+}
+
 // Blocks [b0, b1) of one row through a D-deep register pipeline: the loads of block b+D are issued before block b is
 // computed, so every lane keeps D blocks (D x 48..68 bytes) in flight.  sink(b, terms) is called in block order.
 template <typename Raw, int D, typename Sink>
@@ -506,11 +543,12 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
 }
 
 template <typename Raw, int D>
-__device__ __forceinline__ bool row_kquant_typed(const DevMat& w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
+__device__ __forceinline__ bool row_kquant_typed(const DevMat w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
   const int t = lane & 3, nb = w.nb;
   const size_t rb = (size_t)row * nb;
   Fold f{0.f, 0.f, 0.f};
   if (cx.split == 1) {
+    prefetch_row(w, rb, D, nb, t);
     stream_blocks<Raw, D>(w, rb, 0, nb, a, t, [&](int, const BlockTerms& x) { fold_block(f, x); });
     out = fold_finish(w.type, f);
     return true;
@@ -541,9 +579,11 @@ __device__ __forceinline__ bool row_kquant_typed(const DevMat& w, int row, const
   return true;
 }
 
-__device__ __forceinline__ bool row_kquant_split(const DevMat& w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
-  if (w.type == GT_Q4_K) return row_kquant_typed<RawQ4K, 4>(w, row, a, lane, cx, out);
-  if (w.type == GT_Q6_K) return row_kquant_typed<RawQ6K, 3>(w, row, a, lane, cx, out);
+// KT = the one K-quant type of the launch (smaller kernel, no type switch in the loop), or 0 = decide per matrix
+template <int KT>
+__device__ __forceinline__ bool row_kquant_split(const DevMat w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
+  if (KT == GT_Q4_K || (KT == 0 && w.type == GT_Q4_K)) return row_kquant_typed<RawQ4K, 4>(w, row, a, lane, cx, out);
+  if (KT == GT_Q6_K || (KT == 0 && w.type == GT_Q6_K)) return row_kquant_typed<RawQ6K, 3>(w, row, a, lane, cx, out);
   return row_kquant_typed<RawQ5K, 3>(w, row, a, lane, cx, out);
 }
 
@@ -643,16 +683,17 @@ __host__ __device__ inline int rows_per_unit(int type) {
 // ---------------------------------------------------------------------------------------------
 // Persistent: grid = number of SMs, one CTA each.  K-quant launches: `split` consecutive warps share an 8-row tile, a CTA
 // works on MV_WARPS/split tiles per wave.  Other types: warp tasks strided over all warps of the grid.
+template <int KT>
 static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p, const int split) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
   __shared__ float mailbox[MV_WARPS][2][96];   // [receiving warp][gate/up chain][3*32]
   __shared__ int flags[MV_WARPS][2];
   if (threadIdx.x < MV_WARPS * 2) ((int*)flags)[threadIdx.x] = 0;
-  stage_activation(p.x, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
+  stage_activation(p, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
   const ActView a = act_view(p.act, p.K, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool kq = type_is_kquant(p.seg[0].w.type);
+  const bool kq = KT != 0 || type_is_kquant(p.seg[0].w.type);
 
   if (kq) {
     // tile space: all segments concatenated (pair mode: the gate matrix's tiles; each tile also runs the up matrix)
@@ -668,18 +709,19 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
       if (tile < ntiles) {                                  // uniform across the split warps of a tile
         int s = 0;
         while (tile >= tiles_seg[s]) { tile -= tiles_seg[s]; s++; }
-        const MVSeg& sg = p.seg[s];
+        const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
         const int row = tile * MV_KQ_ROWS + (lane >> 2), rc = min(row, sg.w.M - 1);
         SplitCtx cx;
         cx.split = split; cx.slice = slice; cx.wave = wave; cx.buf = buf;
         cx.mail = mailbox[(warp + 1) % MV_WARPS][0]; cx.mail_in = mailbox[warp][0];
         cx.flag_out = &flags[(warp + 1) % MV_WARPS][0]; cx.flag_in = &flags[warp][0];
         float v = 0.f, vu = 0.f;
-        const bool done = row_kquant_split(sg.w, rc, a, lane, cx, v);
+        const bool done = row_kquant_split<KT>(sg.w, rc, a, lane, cx, v);
         if (p.pair_silu) {
           cx.mail = mailbox[(warp + 1) % MV_WARPS][1]; cx.mail_in = mailbox[warp][1];
           cx.flag_out = &flags[(warp + 1) % MV_WARPS][1]; cx.flag_in = &flags[warp][1];
-          row_kquant_split(p.seg[1].w, rc, a, lane, cx, vu);
+          const DevMat um = p.seg[1].w;
+          row_kquant_split<KT>(um, rc, a, lane, cx, vu);
           if (done && (lane & 3) == 0 && row < sg.w.M) sg.out[row] = __fmul_rn(table_f16(p.silu_tab, v), vu);
         } else if (done && (lane & 3) == 0 && row < sg.w.M) {
           store_epilogue(sg, p, row, v);
@@ -689,6 +731,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
     }
     return;
   }
+  if (KT != 0) return;   // specialised instances carry no code for the other weight types
 
   const int gw = blockIdx.x * MV_WARPS + warp, nw = gridDim.x * MV_WARPS;
   if (p.pair_silu) {
@@ -724,7 +767,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
 }
 
 // host-side launch geometry shared by the engine and the op-level entry points
-struct MVLaunch { int split; int grid; size_t smem; };
+struct MVLaunch { int split; int grid; size_t smem; int kt; };
 inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
   MVLaunch L;
   const size_t act = (act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15;
@@ -733,11 +776,15 @@ inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
   long units = 0;
   for (int s = 0; s < nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
   L.split = 1;
+  L.kt = 0;
   if (kq) {
+    L.kt = p.seg[0].w.type;
+    for (int s = 1; s < p.nseg; s++) if (p.seg[s].w.type != L.kt) L.kt = 0;
+    // K-split only when there are fewer tiles than warps (the ordered hand-off costs instructions; measured slower otherwise)
     const int nb = p.K / 256;
     const long warps = (long)n_sm * MV_WARPS;
-    while (L.split < 8 && units * L.split * 4 < warps * 3 && nb / (L.split * 2) >= 2) L.split *= 2;   // give ~every warp a task
-    while (L.split < 8 && (nb + L.split - 1) / L.split > MV_SPLIT_MAXB && L.split > 1) L.split *= 2;
+    while (L.split < 8 && units * L.split * 4 < warps * 3 && nb / (L.split * 2) >= 2) L.split *= 2;
+    while (L.split < 8 && (nb + L.split - 1) / L.split > MV_SPLIT_MAXB) L.split *= 2;
     const int tpw = MV_WARPS / L.split;
     L.grid = (int)std::max<long>(1, std::min<long>((units + tpw - 1) / tpw, (long)n_sm));
     L.smem = act + (L.split > 1 ? (size_t)MV_WARPS * MV_SPLIT_MAXB * 160 * 4 : 0);
@@ -746,6 +793,24 @@ inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
     L.smem = act;
   }
   return L;
+}
+
+
+// static: each translation unit launches / configures ITS OWN instantiations of the (static) kernel template
+static inline void launch_matvec_kernel(const MVLaunch& L, cudaStream_t st, const MVParams& p) {
+  switch (L.kt) {
+    case GT_Q4_K: k_matvec<GT_Q4_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
+    case GT_Q5_K: k_matvec<GT_Q5_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
+    case GT_Q6_K: k_matvec<GT_Q6_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
+    default: k_matvec<0><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
+  }
+}
+static inline cudaError_t matvec_set_smem_limit(int bytes) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_matvec<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q4_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q5_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_matvec<GT_Q6_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 }  // namespace ctb

@@ -93,13 +93,13 @@ void run_matvec(MVParams& p) {
   p.gelu_tab = tables().gelu;
   static bool attr = false;
   if (!attr) {
-    OPS_CUDA(cudaFuncSetAttribute(k_matvec, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OPS_CUDA(matvec_set_smem_limit(200 * 1024));
     attr = true;
   }
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
   const MVLaunch L = matvec_launch_shape(p, n_sm);
-  k_matvec<<<L.grid, MV_THREADS, L.smem, 0>>>(p, L.split);
+  launch_matvec_kernel(L, 0, p);
   OPS_CUDA(cudaGetLastError());
 }
 
@@ -108,7 +108,9 @@ __global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const
                                                             uint8_t* dump) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
-  stage_activation(x, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
+  MVParams q{};
+  q.x = x;
+  stage_activation(q, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
   const size_t n = act_smem_bytes(act, K);
   for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
 }
