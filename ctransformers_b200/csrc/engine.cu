@@ -287,8 +287,10 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
   launches_per_step_ = 0;
   mark(-1);
-  k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
-  launches_per_step_++;
+  if (!matvec_only_) {
+    k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
+    launches_per_step_++;
+  }
   mark(3);
   float* x = xa_;
   float* y = xb_;
@@ -317,7 +319,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         }
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
-      k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      if (!matvec_only_) k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
       mark(1);
       launches_per_step_ += 1;
       {  // wo + residual
@@ -362,7 +364,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         launch_matvec(p);
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
-      k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      if (!matvec_only_) k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
       mark(1);
       launches_per_step_ += 1;
       {  // attention output projection
@@ -386,7 +388,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
     p.norm_out = d_embd_; p.act = act_format_for(output_.type); p.nseg = 1;
     p.seg[0] = seg(output_, d_logits_);
     launch_matvec(p);
-    if (greedy) {
+    if (greedy && !matvec_only_) {
       k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
       k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
       launches_per_step_ += 2;
@@ -425,6 +427,39 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
   for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
   prof_ev_.clear(); prof_kind_.clear();
   return n;
+}
+
+// The step's mat-vec launches alone (same kernels, same parameters, same order, no attention / embedding / argmax), replayed
+// as a CUDA graph: their summed duration under in-graph launch conditions is what bench.py's roofline for k_matvec uses.
+double Engine::time_matvec_only(int reps, long* launches) {
+  CTB_CUDA(cudaSetDevice(device_));
+  cudaStream_t user = stream_, cap;
+  CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const long keep = launches_per_step_;
+  cudaGraphExec_t ex = nullptr;
+  stream_ = cap; matvec_only_ = true;
+  try {
+    cudaGraph_t g;
+    CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    enqueue_step(true, false);
+    CTB_CUDA(cudaStreamEndCapture(cap, &g));
+    CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+  } catch (...) { stream_ = user; matvec_only_ = false; launches_per_step_ = keep; cudaStreamDestroy(cap); throw; }
+  if (launches) *launches = launches_per_step_;
+  stream_ = user; matvec_only_ = false; launches_per_step_ = keep;
+  cudaStreamDestroy(cap);
+  cudaEvent_t e0, e1;
+  CTB_CUDA(cudaEventCreate(&e0)); CTB_CUDA(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; i++) CTB_CUDA(cudaGraphLaunch(ex, stream_));
+  CTB_CUDA(cudaEventRecord(e0, stream_));
+  for (int i = 0; i < reps; i++) CTB_CUDA(cudaGraphLaunch(ex, stream_));
+  CTB_CUDA(cudaEventRecord(e1, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaGraphExecDestroy(ex);
+  return (double)ms / reps;
 }
 
 void Engine::destroy_graphs() {

@@ -49,6 +49,7 @@ class Engine {
   double decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens);
   // One eager (un-graphed) decode step at n_past with a CUDA event after every kernel; accumulates the
   // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
+  double time_matvec_only(int reps, long* launches);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
 
   float* logits() { return h_logits_; }
@@ -100,6 +101,7 @@ class Engine {
   void destroy_graphs();
   void launch_matvec(struct MVParams& p);
   bool profiling_ = false;
+  bool matvec_only_ = false;
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<int> prof_kind_;
   void mark(int kind);

@@ -196,6 +196,15 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
   }
 }
 
+double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches) {
+  try {
+    return llm->engine->time_matvec_only(reps < 1 ? 1 : reps, launches);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "ctransformers-b200: time_matvec_only failed: %s\n", e.what());
+    return -1.0;
+  }
+}
+
 // ---- host-only logic (no GPU needed): tokenizer / detokenizer / sampler on their own
 struct ctb_vocab { std::unique_ptr<GGUFFile> file; Vocab vocab; };
 

@@ -69,6 +69,10 @@ double ctb_llm_decode_greedy(LLM* llm, int first_token, int n_past, int n_steps,
 /* One eager decode step with a CUDA event after every kernel; ADDS device milliseconds and launch counts per class into
  * ms_by_kind[4] / count_by_kind[4] (0 mat-vec, 1 attention, 2 rope+kv store, 3 other).  Returns kernels timed, < 0 on error. */
 int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, int* count_by_kind);
+/* The mat-vec launches of one decode step alone (same kernels, parameters and order; attention, embedding and argmax left
+ * out), replayed reps times as a CUDA graph between two CUDA events: returns milliseconds per step, < 0 on error;
+ * *launches = mat-vec launches per step.  KV cache and logits are not meaningful afterwards. */
+double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches);
 
 /* Host-only pieces of the boundary, callable without a GPU: the GGUF vocabulary with its SPM / BPE tokenizer
  * (llama.cpp:1648-1760, 3080-3427, 6151-6187) and the sampler chain of llama_llm::Sample (llama.cc:53-84). */
