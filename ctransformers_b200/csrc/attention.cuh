@@ -186,6 +186,8 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   __shared__ double red_d[ATTN_WARPS];
   const int h = blockIdx.x, n = blockIdx.y, cg = blockIdx.z;
   const int hd = p.hd, per = hd >> 5;
+  pdl_trigger();
+  pdl_wait();
   const int pos = p.state[1] + n;
   if (pos >= p.n_ctx) return;
   const int T = pos + 1;

@@ -63,6 +63,12 @@ __device__ __forceinline__ int2 ldg_stream8(const void* p) {
   return r;
 }
 
+// Programmatic dependent launch (sm_90+): a kernel lets its successor's CTAs start early (they prefetch weights and set up
+// while this one drains) and the successor blocks in pdl_wait() until the whole predecessor grid has finished and its
+// writes are visible.  Both are no-ops for a kernel launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -239,6 +239,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
+  if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
   CTB_CUDA(matvec_set_smem_limit(200 * 1024));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
@@ -266,11 +267,22 @@ void Engine::set_stream(cudaStream_t s) {
   own_stream_ = false;
 }
 
+void Engine::launch_attn(const AttnParams& ap) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(hp_.n_head, 1, hp_.head_dim() / ATTN_CH); cfg.blockDim = dim3(ATTN_THREADS);
+  cfg.dynamicSmemBytes = attn_smem_bytes(hp_.n_ctx, hp_.head_dim()); cfg.stream = stream_;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_ ? 1 : 0;
+  CTB_CUDA(cudaLaunchKernelEx(&cfg, k_attn, ap));
+}
+
 void Engine::launch_matvec(MVParams& p) {
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
   const MVLaunch L = matvec_launch_shape(p, sm_count_);
-  launch_matvec_kernel(L, stream_, p);
+  CTB_CUDA(launch_matvec_kernel(L, stream_, p, pdl_));
   launches_per_step_++;
   mark(0);
 }
@@ -319,7 +331,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         }
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
-      if (!matvec_only_) k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      if (!matvec_only_) launch_attn(ap);
       mark(1);
       launches_per_step_ += 1;
       {  // wo + residual
@@ -364,7 +376,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         launch_matvec(p);
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
-      if (!matvec_only_) k_attn<<<dim3(hp_.n_head, 1, hd / ATTN_CH), ATTN_THREADS, attn_smem_bytes(hp_.n_ctx, hd), stream_>>>(ap);
+      if (!matvec_only_) launch_attn(ap);
       mark(1);
       launches_per_step_ += 1;
       {  // attention output projection

@@ -100,8 +100,10 @@ class Engine {
   void build_graphs();
   void destroy_graphs();
   void launch_matvec(struct MVParams& p);
+  void launch_attn(const struct AttnParams& ap);
   bool profiling_ = false;
   bool matvec_only_ = false;
+  bool pdl_ = true;            // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<int> prof_kind_;
   void mark(int kind);

@@ -52,7 +52,6 @@ struct MVParams {
   int K;
   int act;               // ACT_*
   int nseg;
-  int pair_silu;         // 1: seg[0] = gate, seg[1] = up, seg[0].out[i] = silu(gate_i) * up_i
   MVSeg seg[MV_MAX_SEG];
   const uint16_t* silu_tab;   // 65536-entry fp16 tables built on the host exactly like ggml.c:4319-4333
   const uint16_t* gelu_tab;
@@ -498,16 +497,14 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
   return __fadd_rn(r, m);
 }
 
-// Row `row` of a K-quant matrix, blocks [b0, b1).  split == 1: the whole row, folded as the blocks are computed.
-// split > 1 (K-split): `slice` of `split` consecutive warps share the row tile; this warp parks its blocks' terms in its
-// private buffer, waits for the fold state of the previous slice (shared-memory mailbox + flag), folds its blocks in order
-// and hands the state on; the last slice finishes.  The fold order is identical to the unsplit one.
-struct SplitCtx {
-  int split, slice, wave;        // wave: monotonically increasing id of this hand-off round
-  float* buf;                    // warp-private [nbs][5][32] floats
-  volatile float* mail;          // [3][32] floats of the chain this warp hands to (indexed by the RECEIVING slice)
-  volatile float* mail_in;       // mailbox this warp receives from
-  volatile int* flag_out;        // set to wave+1 when mail is valid
+// Hand-off of a row tile's fold state between consecutive warps of a CTA (see k_matvec): warp w receives at most one state
+// (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
+constexpr int MV_DEF_MAX = 12;   // most blocks of a mid-row segment whose terms are parked before the state arrives
+struct Chain {
+  float* buf;                    // warp-private [MV_DEF_MAX][5][32] floats
+  volatile float* mail_out;      // [3][32] floats, the NEXT warp's mailbox
+  volatile int* flag_out;
+  volatile float* mail_in;       // this warp's mailbox
   volatile int* flag_in;
 };
 
@@ -519,7 +516,7 @@ __device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0,
     prefetch_l2(w.qs + (rb + b) * 128);
     if (w.type == GT_Q6_K && (b & 1) == 0) prefetch_l2(w.qh + (rb + b) * 64);
     if (w.type == GT_Q5_K && (b & 3) == t) prefetch_l2(w.qh + (rb + b) * 32);
-    if ((b & 7) == t) prefetch_l2(w.sc + (rb + b) * 16);
+    if ((b & 7) == t || b - t == b0) prefetch_l2(w.sc + (rb + b) * 16);
   }
 }
 
@@ -542,37 +539,38 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
   }
 }
 
+// Blocks [b0, b1) of row `row`.  b0 == 0: folded as they are computed.  b0 > 0: the previous warp owns the row's fold
+// state; the terms of up to MV_DEF_MAX blocks are parked in the warp's buffer (all the integer work is done before waiting),
+// then the state is received, the parked terms are folded in order and any further blocks are folded directly.
+// b1 == nb: the row is finished (returns true, value in `out`); else the state is posted to the next warp.
+// The fold order is the reference's for every partition of the row.
 template <typename Raw, int D>
-__device__ __forceinline__ bool row_kquant_typed(const DevMat w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
+__device__ __forceinline__ bool run_segment_typed(const DevMat w, int row, int b0, int b1, const ActView& a, int lane, const Chain& ch, float& out) {
   const int t = lane & 3, nb = w.nb;
   const size_t rb = (size_t)row * nb;
   Fold f{0.f, 0.f, 0.f};
-  if (cx.split == 1) {
-    prefetch_row(w, rb, D, nb, t);
-    stream_blocks<Raw, D>(w, rb, 0, nb, a, t, [&](int, const BlockTerms& x) { fold_block(f, x); });
-    out = fold_finish(w.type, f);
-    return true;
-  }
-  const int nbs = (nb + cx.split - 1) / cx.split, b0 = cx.slice * nbs, b1 = min(nb, b0 + nbs);
-  stream_blocks<Raw, D>(w, rb, b0, b1, a, t, [&](int b, const BlockTerms& x) {
-    float* s = cx.buf + (size_t)(b - b0) * 160 + lane;
-    s[0] = x.p0; s[32] = x.p1; s[64] = x.dd; s[96] = x.pm; s[128] = x.ddm;
-  });
-  if (cx.slice > 0) {
-    while (*cx.flag_in < cx.wave + 1) { }
+  int bd = b0;
+  if (b0 > 0) {
+    bd = min(b1, b0 + MV_DEF_MAX);
+    stream_blocks<Raw, D>(w, rb, b0, bd, a, t, [&](int b, const BlockTerms& x) {
+      float* s = ch.buf + (size_t)(b - b0) * 160 + lane;
+      s[0] = x.p0; s[32] = x.p1; s[64] = x.dd; s[96] = x.pm; s[128] = x.ddm;
+    });
+    while (*ch.flag_in == 0) { }
     __syncwarp();
-    f.a0 = cx.mail_in[lane]; f.a1 = cx.mail_in[32 + lane]; f.am = cx.mail_in[64 + lane];
+    f.a0 = ch.mail_in[lane]; f.a1 = ch.mail_in[32 + lane]; f.am = ch.mail_in[64 + lane];
+    for (int b = b0; b < bd; b++) {
+      const float* s = ch.buf + (size_t)(b - b0) * 160 + lane;
+      BlockTerms x; x.p0 = s[0]; x.p1 = s[32]; x.dd = s[64]; x.pm = s[96]; x.ddm = s[128];
+      fold_block(f, x);
+    }
   }
-  for (int b = b0; b < b1; b++) {
-    const float* s = cx.buf + (size_t)(b - b0) * 160 + lane;
-    BlockTerms x; x.p0 = s[0]; x.p1 = s[32]; x.dd = s[64]; x.pm = s[96]; x.ddm = s[128];
-    fold_block(f, x);
-  }
-  if (cx.slice + 1 < cx.split) {
-    cx.mail[lane] = f.a0; cx.mail[32 + lane] = f.a1; cx.mail[64 + lane] = f.am;
+  stream_blocks<Raw, D>(w, rb, bd, b1, a, t, [&](int, const BlockTerms& x) { fold_block(f, x); });
+  if (b1 < nb) {
+    ch.mail_out[lane] = f.a0; ch.mail_out[32 + lane] = f.a1; ch.mail_out[64 + lane] = f.am;
     __threadfence_block();
     __syncwarp();
-    if (lane == 0) *cx.flag_out = cx.wave + 1;
+    if (lane == 0) *ch.flag_out = 1;
     return false;
   }
   out = fold_finish(w.type, f);
@@ -581,10 +579,10 @@ __device__ __forceinline__ bool row_kquant_typed(const DevMat w, int row, const 
 
 // KT = the one K-quant type of the launch (smaller kernel, no type switch in the loop), or 0 = decide per matrix
 template <int KT>
-__device__ __forceinline__ bool row_kquant_split(const DevMat w, int row, const ActView& a, int lane, const SplitCtx& cx, float& out) {
-  if (KT == GT_Q4_K || (KT == 0 && w.type == GT_Q4_K)) return row_kquant_typed<RawQ4K, 4>(w, row, a, lane, cx, out);
-  if (KT == GT_Q6_K || (KT == 0 && w.type == GT_Q6_K)) return row_kquant_typed<RawQ6K, 3>(w, row, a, lane, cx, out);
-  return row_kquant_typed<RawQ5K, 3>(w, row, a, lane, cx, out);
+__device__ __forceinline__ bool run_segment(const DevMat w, int row, int b0, int b1, const ActView& a, int lane, const Chain& ch, float& out) {
+  if (KT == GT_Q4_K || (KT == 0 && w.type == GT_Q4_K)) return run_segment_typed<RawQ4K, 4>(w, row, b0, b1, a, lane, ch, out);
+  if (KT == GT_Q6_K || (KT == 0 && w.type == GT_Q6_K)) return run_segment_typed<RawQ6K, 3>(w, row, b0, b1, a, lane, ch, out);
+  return run_segment_typed<RawQ5K, 3>(w, row, b0, b1, a, lane, ch, out);
 }
 
 // Q4_0: natural plane; lane l uses word (l & 3) of the block's 16 nibble bytes, low nibbles for l < 4 (elements 4l..4l+3),
@@ -672,79 +670,121 @@ __device__ __forceinline__ void store_epilogue(const MVSeg& sg, const MVParams& 
 }
 
 constexpr int MV_KQ_ROWS = 8;      // K-quants: rows per tile (4 lanes per row)
-constexpr int MV_SPLIT_MAXB = 12;  // K-split: most blocks one slice may own (sizes the per-warp term buffer)
 
 // rows one work unit (one warp task) covers for a weight type
 __host__ __device__ inline int rows_per_unit(int type) {
   if (type == GT_F16 || type == GT_F32) return 1;
   return type_is_kquant(type) ? MV_KQ_ROWS : MV_ROWS;
 }
+// relative cost of one row tile of a K-quant matrix (its bytes per block / 16)
+__host__ __device__ inline int tile_cost(int type) { return type == GT_Q6_K ? 13 : (type == GT_Q5_K ? 11 : 9); }
+
+// The K-quant tile space of a launch: the 8-row tiles of all its matrices, concatenated.
+struct TileSpace {
+  int tiles[MV_MAX_SEG], cost[MV_MAX_SEG], nseg, ntiles;
+  long total;   // Σ tiles·cost
+  __device__ __forceinline__ void init(const MVParams& p) {
+    nseg = p.nseg; ntiles = 0; total = 0;
+#pragma unroll
+    for (int s = 0; s < MV_MAX_SEG; s++) {
+      tiles[s] = s < p.nseg ? (p.seg[s].w.M + MV_KQ_ROWS - 1) / MV_KQ_ROWS : 0;
+      cost[s] = s < p.nseg ? tile_cost(p.seg[s].w.type) : 1;
+      ntiles += tiles[s]; total += (long)tiles[s] * cost[s];
+    }
+  }
+  // matrix a tile of the concatenated space belongs to; `tile` becomes the tile index inside that matrix
+  __device__ __forceinline__ int locate(int& tile) const {
+    static_assert(MV_MAX_SEG == 3, "locate() is written out for three segments");
+    if (tile < tiles[0]) return 0;
+    tile -= tiles[0];
+    if (tile < tiles[1]) return 1;
+    tile -= tiles[1];
+    return 2;
+  }
+  // first tile of CTA c of G: the tile at which the cumulative cost reaches c/G of the total
+  __device__ __forceinline__ int boundary(int c, int G) const {
+    if (c >= G) return ntiles;
+    long target = total * c / G;
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < MV_MAX_SEG; s++) {
+      const long span = (long)tiles[s] * cost[s];
+      if (target < span || s == MV_MAX_SEG - 1) return base + (int)min((long)tiles[s], (target + cost[s] / 2) / cost[s]);
+      target -= span; base += tiles[s];
+    }
+    return ntiles;
+  }
+};
 
 // ---------------------------------------------------------------------------------------------
-// Persistent: grid = number of SMs, one CTA each.  K-quant launches: `split` consecutive warps share an 8-row tile, a CTA
-// works on MV_WARPS/split tiles per wave.  Other types: warp tasks strided over all warps of the grid.
+// Persistent: one CTA per SM.  K-quant launches: CTA c owns a contiguous range of row tiles (cost-balanced); the blocks of
+// those tiles, laid end to end, are cut into MV_WARPS equal contiguous pieces, one per warp, so every warp streams the same
+// number of weight bytes whatever the shape.  A row tile cut between warps is folded in order by handing its fp32 state from
+// warp to warp (run_segment_typed).  A warp first does the tiles it starts at block 0 (it can post their state early), then
+// the tile it joined in the middle.  Other weight types: warp tasks strided over all warps of the grid.
 template <int KT>
-static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p, const int split) {
+static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
-  __shared__ float mailbox[MV_WARPS][2][96];   // [receiving warp][gate/up chain][3*32]
-  __shared__ int flags[MV_WARPS][2];
-  if (threadIdx.x < MV_WARPS * 2) ((int*)flags)[threadIdx.x] = 0;
-  stage_activation(p, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
-  const ActView a = act_view(p.act, p.K, smem);
+  __shared__ float mailbox[MV_WARPS + 1][96];
+  __shared__ int flags[MV_WARPS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool kq = KT != 0 || type_is_kquant(p.seg[0].w.type);
+  if (threadIdx.x <= MV_WARPS) flags[threadIdx.x] = 0;
+  pdl_trigger();
+
+  // ---- this warp's share of the weights, known before any input is: ask L2 for it while the prologue runs
+  TileSpace ts;
+  int T0 = 0, nb = 1, s0 = 0, e0 = 0;
+  if (kq) {
+    ts.init(p);
+    T0 = ts.boundary(blockIdx.x, gridDim.x);
+    const int T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
+    nb = p.K >> 8;
+    const int B = (T1 - T0) * nb, Lw = (B + MV_WARPS - 1) / MV_WARPS;
+    s0 = min(B, warp * Lw); e0 = min(B, s0 + Lw);
+    for (int pos = s0; pos < e0;) {
+      int tile = T0 + pos / nb;
+      const int b0 = pos % nb, len = min(nb - b0, e0 - pos);
+      const int s = ts.locate(tile);
+      const DevMat& w = p.seg[s].w;
+      const int row = min(tile * MV_KQ_ROWS + (lane >> 2), w.M - 1);
+      prefetch_row(w, (size_t)row * nb, b0, b0 + len, lane & 3);
+      pos += len;
+    }
+  }
+
+  pdl_wait();   // everything above touched only weights and shared memory; the input vector is the predecessor's output
+  stage_activation(p, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
+  const ActView a = act_view(p.act, p.K, smem);
 
   if (kq) {
-    // tile space: all segments concatenated (pair mode: the gate matrix's tiles; each tile also runs the up matrix)
-    int tiles_seg[MV_MAX_SEG], ntiles = 0;
-    const int nseg = p.pair_silu ? 1 : p.nseg;
-    for (int s = 0; s < nseg; s++) { tiles_seg[s] = (p.seg[s].w.M + MV_KQ_ROWS - 1) / MV_KQ_ROWS; ntiles += tiles_seg[s]; }
-    const int tpw = MV_WARPS / split;                      // tiles per CTA wave
-    const int slice = warp % split, slot = warp / split;
-    float* buf = (float*)(smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15)) + (size_t)warp * MV_SPLIT_MAXB * 160;
-    int wave = 0;
-    for (int t0 = blockIdx.x * tpw; t0 < ntiles; t0 += gridDim.x * tpw, wave++) {
-      int tile = t0 + slot;
-      if (tile < ntiles) {                                  // uniform across the split warps of a tile
-        int s = 0;
-        while (tile >= tiles_seg[s]) { tile -= tiles_seg[s]; s++; }
-        const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
-        const int row = tile * MV_KQ_ROWS + (lane >> 2), rc = min(row, sg.w.M - 1);
-        SplitCtx cx;
-        cx.split = split; cx.slice = slice; cx.wave = wave; cx.buf = buf;
-        cx.mail = mailbox[(warp + 1) % MV_WARPS][0]; cx.mail_in = mailbox[warp][0];
-        cx.flag_out = &flags[(warp + 1) % MV_WARPS][0]; cx.flag_in = &flags[warp][0];
-        float v = 0.f, vu = 0.f;
-        const bool done = row_kquant_split<KT>(sg.w, rc, a, lane, cx, v);
-        if (p.pair_silu) {
-          cx.mail = mailbox[(warp + 1) % MV_WARPS][1]; cx.mail_in = mailbox[warp][1];
-          cx.flag_out = &flags[(warp + 1) % MV_WARPS][1]; cx.flag_in = &flags[warp][1];
-          const DevMat um = p.seg[1].w;
-          row_kquant_split<KT>(um, rc, a, lane, cx, vu);
-          if (done && (lane & 3) == 0 && row < sg.w.M) sg.out[row] = __fmul_rn(table_f16(p.silu_tab, v), vu);
-        } else if (done && (lane & 3) == 0 && row < sg.w.M) {
-          store_epilogue(sg, p, row, v);
-        }
-      }
-      if (split > 1) __syncthreads();   // nobody starts the next hand-off round before every mailbox of this one has been read
+    if (s0 >= e0) return;
+    Chain ch;
+    ch.buf = (float*)(smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15)) + (size_t)warp * MV_DEF_MAX * 160;
+    ch.mail_in = mailbox[warp]; ch.flag_in = &flags[warp];
+    ch.mail_out = mailbox[warp + 1]; ch.flag_out = &flags[warp + 1];
+    const int a0 = s0 % nb;
+    const int def_len = a0 ? min(nb - a0, e0 - s0) : 0;     // the piece of a tile another warp started
+    const int sd = s0 + def_len;                              // tile-aligned from here on
+    const int ndirect = (e0 - sd + nb - 1) / nb;
+    const int nsegs = ndirect + (def_len ? 1 : 0);
+    for (int i = 0; i < nsegs; i++) {
+      int tile, b0, b1;
+      if (i < ndirect) { const int pos = sd + i * nb; tile = T0 + pos / nb; b0 = 0; b1 = min(nb, e0 - pos); }
+      else { tile = T0 + s0 / nb; b0 = a0; b1 = a0 + def_len; }
+      const int s = ts.locate(tile);
+      const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
+      const int row = tile * MV_KQ_ROWS + (lane >> 2);
+      float v = 0.f;
+      const bool done = run_segment<KT>(sg.w, min(row, sg.w.M - 1), b0, b1, a, lane, ch, v);
+      if (done && (lane & 3) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
     }
     return;
   }
   if (KT != 0) return;   // specialised instances carry no code for the other weight types
 
   const int gw = blockIdx.x * MV_WARPS + warp, nw = gridDim.x * MV_WARPS;
-  if (p.pair_silu) {
-    const DevMat& gm = p.seg[0].w;
-    const DevMat& um = p.seg[1].w;
-    const int units = (gm.M + MV_ROWS - 1) / MV_ROWS;
-    for (int un = gw; un < units; un += nw) {
-      const int row = un * MV_ROWS + (lane >> 3), rc = min(row, gm.M - 1);
-      const float vg = dot_legacy(gm, rc, a, lane & 7), vu = dot_legacy(um, rc, a, lane & 7);
-      if ((lane & 7) == 0 && row < gm.M) p.seg[0].out[row] = __fmul_rn(table_f16(p.silu_tab, vg), vu);
-    }
-    return;
-  }
   int first = gw;   // global striding continues across segments so all warps stay busy
   for (int s = 0; s < p.nseg; s++) {
     const MVSeg& sg = p.seg[s];
@@ -767,27 +807,19 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
 }
 
 // host-side launch geometry shared by the engine and the op-level entry points
-struct MVLaunch { int split; int grid; size_t smem; int kt; };
+struct MVLaunch { int grid; size_t smem; int kt; };
 inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
   MVLaunch L;
   const size_t act = (act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15;
-  const int nseg = p.pair_silu ? 1 : p.nseg;
   const bool kq = type_is_kquant(p.seg[0].w.type);
   long units = 0;
-  for (int s = 0; s < nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
-  L.split = 1;
+  for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
   L.kt = 0;
   if (kq) {
     L.kt = p.seg[0].w.type;
     for (int s = 1; s < p.nseg; s++) if (p.seg[s].w.type != L.kt) L.kt = 0;
-    // K-split only when there are fewer tiles than warps (the ordered hand-off costs instructions; measured slower otherwise)
-    const int nb = p.K / 256;
-    const long warps = (long)n_sm * MV_WARPS;
-    while (L.split < 8 && units * L.split * 4 < warps * 3 && nb / (L.split * 2) >= 2) L.split *= 2;
-    while (L.split < 8 && (nb + L.split - 1) / L.split > MV_SPLIT_MAXB) L.split *= 2;
-    const int tpw = MV_WARPS / L.split;
-    L.grid = (int)std::max<long>(1, std::min<long>((units + tpw - 1) / tpw, (long)n_sm));
-    L.smem = act + (L.split > 1 ? (size_t)MV_WARPS * MV_SPLIT_MAXB * 160 * 4 : 0);
+    L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm));
+    L.smem = act + (size_t)MV_WARPS * MV_DEF_MAX * 160 * 4;
   } else {
     L.grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)n_sm));
     L.smem = act;
@@ -797,12 +829,18 @@ inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
 
 
 // static: each translation unit launches / configures ITS OWN instantiations of the (static) kernel template
-static inline void launch_matvec_kernel(const MVLaunch& L, cudaStream_t st, const MVParams& p) {
+static inline cudaError_t launch_matvec_kernel(const MVLaunch& L, cudaStream_t st, const MVParams& p, bool pdl = false) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(MV_THREADS); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
   switch (L.kt) {
-    case GT_Q4_K: k_matvec<GT_Q4_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
-    case GT_Q5_K: k_matvec<GT_Q5_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
-    case GT_Q6_K: k_matvec<GT_Q6_K><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
-    default: k_matvec<0><<<L.grid, MV_THREADS, L.smem, st>>>(p, L.split); break;
+    case GT_Q4_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q4_K>, p);
+    case GT_Q5_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q5_K>, p);
+    case GT_Q6_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q6_K>, p);
+    default: return cudaLaunchKernelEx(&cfg, k_matvec<0>, p);
   }
 }
 static inline cudaError_t matvec_set_smem_limit(int bytes) {

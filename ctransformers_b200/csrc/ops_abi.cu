@@ -99,7 +99,7 @@ void run_matvec(MVParams& p) {
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
   const MVLaunch L = matvec_launch_shape(p, n_sm);
-  launch_matvec_kernel(L, 0, p);
+  OPS_CUDA(launch_matvec_kernel(L, 0, p));
   OPS_CUDA(cudaGetLastError());
 }
 
@@ -113,6 +113,17 @@ __global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const
   stage_activation(q, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
   const size_t n = act_smem_bytes(act, K);
   for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
+}
+
+// the x_mode = 1 input path of the prologue on its own: out[i] = silu_table(gate[i]) * up[i]
+__global__ void __launch_bounds__(MV_THREADS) k_gate_dump(const float* gate, const float* up, const uint16_t* silu_tab, int M, float* out) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ double red[MV_WARPS];
+  MVParams q{};
+  q.x = gate; q.x2 = up; q.x_mode = 1; q.silu_tab = silu_tab;
+  stage_activation(q, nullptr, nullptr, nullptr, NORM_NONE, 0.f, M, ACT_F32, smem, red, false);
+  const float* f = (const float*)smem;
+  for (int i = threadIdx.x; i < M; i += MV_THREADS) out[i] = f[i];
 }
 
 int guarded(const char* what, const std::function<void()>& fn) {
@@ -282,12 +293,17 @@ int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const f
     OwnedMat w1, w3;
     upload(w1, type, w1_blocks, K, M);
     upload(w3, type, w3_blocks, K, M);
-    DevBuf dx((size_t)K * 4), dy((size_t)M * 4);
+    DevBuf dx((size_t)K * 4), dg((size_t)M * 4), du((size_t)M * 4), dy((size_t)M * 4);
     OPS_CUDA(cudaMemcpy(dx.p, x, (size_t)K * 4, cudaMemcpyHostToDevice));
+    // as the engine does it: gate and up rows in one launch, SiLU(gate)*up where the down projection stages its input
     MVParams p{};
-    p.x = dx.as<float>(); p.norm_mode = NORM_NONE; p.K = K; p.act = act_format_for(type); p.nseg = 2; p.pair_silu = 1;
-    p.seg[0].w = w1.m; p.seg[0].out = dy.as<float>(); p.seg[1].w = w3.m;
+    p.x = dx.as<float>(); p.norm_mode = NORM_NONE; p.K = K; p.act = act_format_for(type); p.nseg = 2;
+    p.seg[0].w = w1.m; p.seg[0].out = dg.as<float>(); p.seg[1].w = w3.m; p.seg[1].out = du.as<float>();
     run_matvec(p);
+    const size_t smem = (size_t)M * 4 + 64;
+    OPS_CUDA(cudaFuncSetAttribute(k_gate_dump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    k_gate_dump<<<1, MV_THREADS, smem>>>(dg.as<float>(), du.as<float>(), tables().silu, M, dy.as<float>());
+    OPS_CUDA(cudaGetLastError());
     OPS_CUDA(cudaMemcpy(out, dy.p, (size_t)M * 4, cudaMemcpyDeviceToHost));
   });
 }
