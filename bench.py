@@ -12,10 +12,12 @@ prefilled untimed, then W warm-up + K timed decode steps.
             launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling)
   e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, logits D2H and the
             host sampler inside the timed region
-  roofline  HBM: algorithmic weight+KV bytes per step ÷ step time, against MEASURED_PEAKS.json hbm_gbs; plus the mat-vec
-            kernels alone from an eager pass with a CUDA event after every kernel
+  roofline  dominant kernel k_matvec (HBM-bound): the GGUF bytes of the weights its 161 launches of a step read (4005.4 MB) ÷ their
+            duration, measured live by replaying exactly those launches as a CUDA graph between CUDA events on the engine's
+            stream; peak = MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes per launch (profiles/k_matvec_traffic.json).
+            roofline.step = the same for the whole step (weights + KV + logits bytes ÷ device-timed step)
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref/libctransformers_ref.so) on the host cores, same
-            model file, same prompt, bounded sample.
+            model file, same prompt, bounded sample, thread count swept (ggml's spin-wait pool collapses when oversubscribed).
 """
 import argparse
 import ctypes as C
@@ -100,6 +102,23 @@ def kv_bytes_per_step(n_layer, n_embd_gqa, t_avg):
     return 2 * n_layer * n_embd_gqa * t_avg * 2 + 2 * n_layer * n_embd_gqa * 2
 
 
+def pick_threads(llm, tok, cores):
+    """ggml's spinning thread pool degrades badly when oversubscribed; sweep like BASELINE.md's plan and keep the fastest."""
+    forced = os.environ.get("CTB_REF_THREADS")
+    if forced:
+        return max(1, min(cores, int(forced))), {}
+    cands = sorted({c for c in (4, 8, 16, 24, 32, 48, 64, cores // 2, cores) if 1 <= c <= cores})
+    timing = {}
+    for c in cands:
+        t0 = time.perf_counter()
+        for _ in range(2):
+            llm.eval([tok], threads=c)
+        timing[c] = (time.perf_counter() - t0) / 2
+        if timing[c] > 4 * min(timing.values()):
+            break                      # far past the optimum, more threads only get slower
+    return min(timing, key=timing.get), {str(k): round(v, 4) for k, v in timing.items()}
+
+
 def run_reference(args, rank, world, barrier):
     """The reference's own CPU implementation on the host cores (rank 0 only)."""
     if rank != 0:
@@ -109,27 +128,32 @@ def run_reference(args, rank, world, barrier):
         return
     from ctransformers_b200 import AutoModelForCausalLM
     cores = os.cpu_count() or 1
-    threads = max(1, min(cores, int(os.environ.get("CTB_REF_THREADS", cores))))
     p = ensure_model(0, 1, lambda: None)
-    llm = AutoModelForCausalLM.from_pretrained(str(p), lib=str(REF_SO), context_length=CTX, threads=threads)
+    llm = AutoModelForCausalLM.from_pretrained(str(p), lib=str(REF_SO), context_length=CTX, threads=min(cores, 16))
     ids = prompt_ids()
-    llm.eval(ids, batch_size=256)           # untimed prefill, one chunk
+    llm.eval(ids, batch_size=256, threads=min(cores, 32))           # untimed prefill, one chunk
     tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
-    steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 1))
+    threads, sweep = pick_threads(llm, tok, cores)
+    steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 2 * len(sweep) - 1))
     for _ in range(args.warmup):
-        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        llm.eval([tok], threads=threads); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
     t0 = time.perf_counter()
     for _ in range(steps):
-        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        llm.eval([tok], threads=threads); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
     dt = time.perf_counter() - t0
     v = steps / dt
     print(json.dumps({
-        "impl": "reference", "metric": "decode tokens/s Llama-2-7B Q4_K_M b=1", "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "q4_K/q6_K x q8_K (int8 dot, fp32 combine)",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE,
         "data": "synthetic", "config": workload_config(1),
-        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "reference", "sample": f"{steps} decode steps at context {PROMPT}+ after a {PROMPT}-token prompt, llm.eval+llm.sample, {threads} threads"},
+        "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "reference", "host_cores": cores, "thread_sweep_s_per_token": sweep,
+                         "sample": f"{steps} decode steps at context {PROMPT}+ after a {PROMPT}-token prompt, llm.eval+llm.sample, unmodified reference CPU build (AVX2), {threads} threads (best of the sweep)"},
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+METRIC = "decode tokens/s Llama-2-7B Q4_K_M b=1"
+DTYPE = "int8 (q4_K/q6_K weights x q8_K activations, dp4a), fp32 combine"
 
 
 def workload_config(n):
@@ -231,22 +255,32 @@ def main():
     prof_steps = 4
     for i in range(prof_steps):
         llm.ctb_llm_profile_step(tokens_dev[i], PROMPT + W + steps // 2 + i - prof_steps, ms_kind, cnt_kind)
-    mv_ms_per_step = ms_kind[0] / prof_steps
+    # dominant kernel = k_matvec: its launches of one step alone, replayed as a CUDA graph between two CUDA events on the
+    # engine's stream (after everything else, so the KV cache it leaves behind does not matter)
+    n_mv = C.c_long(0)
+    mv_ms = llm.ctb_llm_time_matvec_only(32, C.byref(n_mv))
+    mv_ms = max_over_ranks(mv_ms)
+    n_mv = max(1, n_mv.value)
+    mv_achieved = wbytes / (mv_ms / 1e3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "k_matvec_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch_avg")
     roofline = {
-        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-        "peak_source": peak_src, "bytes_per_step": step_bytes, "weight_bytes_per_step": wbytes,
-        "frac_vs_3.9GB_weights_only": (3.9e9 / (ms / 1e3 / steps) / 1e9) / peak,
-        "kernel": "k_matvec (quantized mat-vec; all %d launches of a step)" % (cnt_kind[0] // prof_steps),
-        "kernel_only": {"achieved": wbytes / (mv_ms_per_step / 1e3) / 1e9 if mv_ms_per_step > 0 else None,
-                        "frac": (wbytes / (mv_ms_per_step / 1e3) / 1e9) / peak if mv_ms_per_step > 0 else None,
-                        "ms_per_step": {"matvec": ms_kind[0] / prof_steps, "attention": ms_kind[1] / prof_steps, "rope_kv": ms_kind[2] / prof_steps, "other": ms_kind[3] / prof_steps},
-                        "how": f"eager pass, CUDA event after every kernel, {prof_steps} steps"},
+        "bound": "hbm", "kernel": "k_matvec", "achieved": mv_achieved, "peak": peak, "unit": "GB/s", "frac": mv_achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "launches_per_step": n_mv, "algorithmic_bytes_per_launch": wbytes / n_mv, "avg_launch_us": 1e3 * mv_ms / n_mv,
+        "how": "weight bytes of the step's k_matvec launches / their duration: the same launches (no attention, embedding, argmax) replayed as a CUDA graph, CUDA events on the launching stream, 32 replays",
+        "step": {"achieved": achieved, "frac": achieved / peak, "bytes_per_step": step_bytes, "weight_bytes_per_step": wbytes,
+                 "frac_vs_3.9GB_weights_only": (3.9e9 / (ms / 1e3 / steps) / 1e9) / peak,
+                 "how": "weights + KV + logits bytes of a whole decode step / device-timed step (all kernels)"},
+        "eager_ms_per_step_by_kind": {"matvec": ms_kind[0] / prof_steps, "attention": ms_kind[1] / prof_steps, "other": ms_kind[3] / prof_steps,
+                                      "how": f"eager pass, CUDA event after every kernel, {prof_steps} steps (kernel share of the step)"},
     }
 
     result = {
-        "metric": "decode tokens/s Llama-2-7B Q4_K_M b=1", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": W,
+        "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": W,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "q4_K/q6_K x q8_K (int8 dp4a dot, fp32 combine)", "data": "synthetic", "config": workload_config(world),
+        "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": shape.n_vocab * 4 + shape.n_embd * 4,
                 "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs"},
@@ -258,18 +292,18 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline and REF_SO.exists():
         del llm
         cores = os.cpu_count() or 1
-        ref = AutoModelForCausalLM.from_pretrained(str(path), lib=str(REF_SO), context_length=CTX, threads=cores)
+        ref = AutoModelForCausalLM.from_pretrained(str(path), lib=str(REF_SO), context_length=CTX, threads=min(cores, 16))
         n_prompt, n_dec = 32, 12
-        ref.eval(ids[:n_prompt], batch_size=32)
+        ref.eval(ids[:n_prompt], batch_size=32, threads=min(cores, 32))
         t = ref.sample(top_k=1, repetition_penalty=1.0, seed=0)
-        ref.eval([t])
+        threads, sweep = pick_threads(ref, t, cores)
         t0 = time.perf_counter()
         for _ in range(n_dec):
             t = ref.sample(top_k=1, repetition_penalty=1.0, seed=0)
-            ref.eval([t])
+            ref.eval([t], threads=threads)
         dt = time.perf_counter() - t0
-        result["cpu_baseline"] = {"value": n_dec / dt, "unit": "tokens/s", "cores": cores, "kind": "reference",
-                                  "sample": f"{n_dec} decode steps after a {n_prompt}-token prompt (context ≈{n_prompt + n_dec}), same model file, unmodified reference CPU build (AVX2), {cores} threads"}
+        result["cpu_baseline"] = {"value": n_dec / dt, "unit": "tokens/s", "cores": threads, "kind": "reference", "host_cores": cores, "thread_sweep_s_per_token": sweep,
+                                  "sample": f"{n_dec} decode steps after a {n_prompt}-token prompt (context ≈{n_prompt + 2 * len(sweep) + n_dec}), same model file, unmodified reference CPU build (AVX2), {threads} threads (best of the sweep)"}
     if rank == 0:
         print(json.dumps(result))
     if dist:

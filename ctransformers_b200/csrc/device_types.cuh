@@ -57,6 +57,12 @@ __device__ __forceinline__ int4 ldg_stream16(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// read-only 16-byte load that keeps its place in program order (block headers: re-used by the 4 lanes of a row, L1 may keep them)
+__device__ __forceinline__ int4 ldg_keep16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ int2 ldg_stream8(const void* p) {
   int2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));

@@ -355,17 +355,17 @@ struct RawQ5K { int4 c0, c1, ch; uint32_t hb0, hb1; };
 struct RawQ6K { int4 ql0, ql1, scv; int2 qh0, qh1; uint16_t d; };
 __device__ __forceinline__ void load_raw(RawQ4K& r, const DevMat& w, size_t blk, int t) {
   r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
-  r.ch = __ldg((const int4*)(w.sc + blk * 16));
+  r.ch = ldg_keep16(w.sc + blk * 16);
 }
 __device__ __forceinline__ void load_raw(RawQ5K& r, const DevMat& w, size_t blk, int t) {
   r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
-  r.ch = __ldg((const int4*)(w.sc + blk * 16));
+  r.ch = ldg_keep16(w.sc + blk * 16);
   r.hb0 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + t * 4)); r.hb1 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + 16 + t * 4));
 }
 __device__ __forceinline__ void load_raw(RawQ6K& r, const DevMat& w, size_t blk, int t) {
   r.ql0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.ql1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
   r.qh0 = ldg_stream8(w.qh + blk * 64 + t * 8); r.qh1 = ldg_stream8(w.qh + blk * 64 + 32 + t * 8);
-  r.scv = __ldg((const int4*)(w.sc + blk * 16));
+  r.scv = ldg_keep16(w.sc + blk * 16);
   r.d = __ldg(w.d + blk);
 }
 
@@ -520,8 +520,11 @@ __device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0,
   }
 }
 
-// Blocks [b0, b1) of one row through a D-deep register pipeline: the loads of block b+D are issued before block b is
-// computed, so every lane keeps D blocks (D x 48..68 bytes) in flight.  sink(b, terms) is called in block order.
+// Blocks [b0, b1) of one row through a D-deep register pipeline: slot i of the ring is refilled with block b+D right after
+// block b (which lived in it) has been consumed, so every lane keeps D-1..D blocks (each 48..68 bytes) in flight while it
+// computes.  The compiler barriers pin that order (without them the loads of a whole round are sunk to the end of the round
+// and every round then waits for memory).  sink(b, terms) is called in block order.
+#define CTB_PIN() asm volatile("" ::: "memory")
 template <typename Raw, int D, typename Sink>
 __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0, int b1, const ActView& a, int t, Sink sink) {
   if (b0 >= b1) return;
@@ -532,9 +535,10 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
   for (int b = b0; b < b1; b += D) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
-      const Raw cur = ring[i];
+      CTB_PIN();
+      if (b + i < b1) sink(b + i, block_terms(ring[i], b + i, a, t));
+      CTB_PIN();
       load_raw(ring[i], w, rb + min(b + i + D, last), t);
-      if (b + i < b1) sink(b + i, block_terms(cur, b + i, a, t));
     }
   }
 }
