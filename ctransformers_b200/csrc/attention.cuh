@@ -203,7 +203,6 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   uint16_t* q16 = p16 + cp;                             // [hd] f16 rotated query, K-permuted order
   uint16_t* k16 = q16 + hd;                             // [hd] f16 rotated key of this position, K-permuted order
   uint16_t* v16 = k16 + hd;                             // [hd] f16 value of this position, natural order
-  float* vres = (float*)(v16 + hd);                     // [ATTN_CH]
 
   {  // RoPE (pairs) + f16 conversion of q, k, v for this position
     const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
@@ -287,8 +286,13 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   for (int t = threadIdx.x; t < t_end; t += ATTN_THREADS) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
   __syncthreads();
 
-  // V·P for this CTA's channels.  lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i
+  // V·P for this CTA's channels.  lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i.
+  // leftover part (ggml.c:2415-2418): positions n_vec <= t < T are added one by one in double after the lane reduction.  They
+  // are the row i_left of one 256-position chunk, i.e. element i_left of lanes 0..T-n_vec-1 of that chunk's 16-byte loads:
+  // every lane forms its float product and the warp adds them in lane order through shuffles.
   const int lim = min(T, n_vec);
+  const int n_left = T - n_vec;                       // <= 31; <= 0 when the eval chunk extends past this token
+  const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
   const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
   for (int cc = warp; cc < ATTN_CH; cc += ATTN_WARPS) {
     const int c = cg * ATTN_CH + cc;
@@ -311,19 +315,16 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
       }
     }
     s = attn_reduce_f32x8(s);
-    if (lane == 0) vres[cc] = s;
-  }
-  __syncthreads();
-  // leftover part: positions n_vec <= t < T one by one in double (ggml.c:2415-2418), one thread per channel
-  for (int cc = threadIdx.x; cc < ATTN_CH; cc += ATTN_THREADS) {
-    const int c = cg * ATTN_CH + cc;
-    double sumf = (double)vres[cc];
-    const uint16_t* vrow = vhead + (size_t)c * cp;
-    for (int t = n_vec; t < T; t++) {
-      const uint16_t vh = (t == pos) ? v16[c] : vrow[v_perm(t)];
-      sumf += (double)__fmul_rn(h2f(vh), h2f(p16[v_perm(t)]));
+    double sumf = (double)s;
+    if (n_left > 0) {
+      const int t = n_vec + lane;
+      uint16_t vh = vrow[ch_left * 256 + lane * 8 + i_left];
+      const uint16_t ph = p16[ch_left * 256 + lane * 8 + i_left];
+      if (t == pos) vh = vcur;
+      const float term = __fmul_rn(h2f(vh), h2f(ph));
+      for (int l = 0; l < n_left; l++) sumf += (double)__shfl_sync(0xffffffffu, term, l);
     }
-    p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = (float)sumf;
+    if (lane == 0) p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = (float)sumf;
   }
 }
 

@@ -240,7 +240,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
   if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
-  CTB_CUDA(matvec_set_smem_limit(200 * 1024));
+  CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();

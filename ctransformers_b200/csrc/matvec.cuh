@@ -43,6 +43,7 @@ struct MVSeg {
 struct MVParams {
   const float* x;        // [K] f32 input
   const float* x2;       // x_mode 1: second operand
+  int def_max;           // set by matvec_launch_shape: blocks of parked terms per warp that fit in shared memory
   int x_mode;            // 0: x;  1: silu_table(x) * x2 (ggml_silu + ggml_mul, llama.cpp:2438-2443);  2: gelu_table(x) (falcon)
   const float* norm_w;   // [K] or null
   const float* norm_b;   // [K] or null (LayerNorm bias)
@@ -140,16 +141,23 @@ __device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid,
   }
 }
 
-__device__ __forceinline__ void stage_activation(const MVParams& xs, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
+// Norm weight / bias of this thread's first 16 elements: constants of the model, so they are fetched before the kernel waits
+// for its predecessor (pdl_wait) and are in registers when the input vector arrives.
+struct NormPre { float w0[16], bias0[16]; };
+__device__ __forceinline__ void preload_norm(NormPre& np, const float* nw, const float* nb_, int norm_mode, int K) {
+  const int t = threadIdx.x;
+  if (norm_mode != NORM_NONE && nw) load16(nw + t * 16, K - t * 16, np.w0);
+  if (norm_mode != NORM_NONE && nb_) load16(nb_ + t * 16, K - t * 16, np.bias0);
+}
+
+__device__ __forceinline__ void stage_activation(const MVParams& xs, const NormPre& np, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
                                                   int K, int act, uint8_t* smem, double* red, bool write_norm) {
   const int t = threadIdx.x, lane = t & 31;
   const int passes = (K + MV_THREADS * 16 - 1) / (MV_THREADS * 16);
   // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
   float mean = 0.f, scale = 1.f;
-  float v0[16], w0[16], bias0[16];   // pass 0's x / norm weight / bias stay in registers: all global loads of the prologue are
-  load16x(xs, t * 16, K - t * 16, v0);   // issued here, back to back, and their latencies overlap
-  if (norm_mode != NORM_NONE && nw) load16(nw + t * 16, K - t * 16, w0);
-  if (norm_mode != NORM_NONE && nb_) load16(nb_ + t * 16, K - t * 16, bias0);
+  float v0[16];                          // pass 0's x stays in registers
+  load16x(xs, t * 16, K - t * 16, v0);
   if (norm_mode == NORM_RMS) {
     double ss = 0.0;
     for (int ps = 0; ps < passes; ps++) {
@@ -205,7 +213,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const float
       float w[16], bb[16];
       if (ps == 0) {
 #pragma unroll
-        for (int e = 0; e < 16; e++) { w[e] = w0[e]; bb[e] = bias0[e]; }
+        for (int e = 0; e < 16; e++) { w[e] = np.w0[e]; bb[e] = np.bias0[e]; }
       } else {
         if (nw) load16(nw + base, valid, w);
         if (nb_) load16(nb_ + base, valid, bb);
@@ -349,7 +357,7 @@ __device__ __forceinline__ ActBlock load_act_block(const ActView& a, int b, int 
 // and the mins term pm·ddm (Q4_K: mins lane k = t; Q5_K: the scalar term, lane t == 0; Q6_K: none).
 struct BlockTerms { float p0, p1, dd, pm, ddm; };
 
-// Raw block data of one lane (kept in registers by the software pipeline below)
+// Raw block data of one lane, held in registers by the software pipeline below
 struct RawQ4K { int4 c0, c1, ch; };
 struct RawQ5K { int4 c0, c1, ch; uint32_t hb0, hb1; };
 struct RawQ6K { int4 ql0, ql1, scv; int2 qh0, qh1; uint16_t d; };
@@ -499,9 +507,12 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 
 // Hand-off of a row tile's fold state between consecutive warps of a CTA (see k_matvec): warp w receives at most one state
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
+constexpr int MV_SMEM_LIMIT = 220 * 1024;   // dynamic shared memory a launch may ask for (227 KB per CTA minus the static part)
 constexpr int MV_DEF_MAX = 12;   // most blocks of a mid-row segment whose terms are parked before the state arrives
+constexpr int MV_RING = 2;       // blocks per lane in flight in the register pipeline (measured: 2 > 3 > 1 > 4 once L2 is prefetched)   // most blocks of a mid-row segment whose terms are parked before the state arrives
 struct Chain {
-  float* buf;                    // warp-private [MV_DEF_MAX][5][32] floats
+  float4* buf;                   // warp-private [def_max][32] parked block terms
+  int def_max;
   volatile float* mail_out;      // [3][32] floats, the NEXT warp's mailbox
   volatile int* flag_out;
   volatile float* mail_in;       // this warp's mailbox
@@ -520,13 +531,11 @@ __device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0,
   }
 }
 
-// Blocks [b0, b1) of one row through a D-deep register pipeline: slot i of the ring is refilled with block b+D right after
-// block b (which lived in it) has been consumed, so every lane keeps D-1..D blocks (each 48..68 bytes) in flight while it
-// computes.  The compiler barriers pin that order (without them the loads of a whole round are sunk to the end of the round
-// and every round then waits for memory).  sink(b, terms) is called in block order.
 #define CTB_PIN() asm volatile("" ::: "memory")
-template <typename Raw, int D, typename Sink>
-__device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0, int b1, const ActView& a, int t, Sink sink) {
+template <typename Raw, typename Sink>
+__device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0, int b1, const ActView& a, int lane, Sink sink) {
+  constexpr int D = MV_RING;
+  const int t = lane & 3;
   if (b0 >= b1) return;
   Raw ring[D];
   const int last = b1 - 1;
@@ -543,33 +552,36 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
   }
 }
 
+
 // Blocks [b0, b1) of row `row`.  b0 == 0: folded as they are computed.  b0 > 0: the previous warp owns the row's fold
 // state; the terms of up to MV_DEF_MAX blocks are parked in the warp's buffer (all the integer work is done before waiting),
 // then the state is received, the parked terms are folded in order and any further blocks are folded directly.
 // b1 == nb: the row is finished (returns true, value in `out`); else the state is posted to the next warp.
 // The fold order is the reference's for every partition of the row.
-template <typename Raw, int D>
+template <typename Raw>
 __device__ __forceinline__ bool run_segment_typed(const DevMat w, int row, int b0, int b1, const ActView& a, int lane, const Chain& ch, float& out) {
-  const int t = lane & 3, nb = w.nb;
+  const int nb = w.nb;
   const size_t rb = (size_t)row * nb;
   Fold f{0.f, 0.f, 0.f};
   int bd = b0;
   if (b0 > 0) {
-    bd = min(b1, b0 + MV_DEF_MAX);
-    stream_blocks<Raw, D>(w, rb, b0, bd, a, t, [&](int b, const BlockTerms& x) {
-      float* s = ch.buf + (size_t)(b - b0) * 160 + lane;
-      s[0] = x.p0; s[32] = x.p1; s[64] = x.dd; s[96] = x.pm; s[128] = x.ddm;
+    bd = min(b1, b0 + ch.def_max);
+    // parked per block and lane: {p0, p1, pm, (t == 0 ? dd : ddm)} — dd and ddm are the same for the 4 lanes of a row
+    stream_blocks<Raw>(w, rb, b0, bd, a, lane, [&](int b, const BlockTerms& x) {
+      ch.buf[(size_t)(b - b0) * 32 + lane] = make_float4(x.p0, x.p1, x.pm, (lane & 3) == 0 ? x.dd : x.ddm);
     });
     while (*ch.flag_in == 0) { }
     __syncwarp();
     f.a0 = ch.mail_in[lane]; f.a1 = ch.mail_in[32 + lane]; f.am = ch.mail_in[64 + lane];
     for (int b = b0; b < bd; b++) {
-      const float* s = ch.buf + (size_t)(b - b0) * 160 + lane;
-      BlockTerms x; x.p0 = s[0]; x.p1 = s[32]; x.dd = s[64]; x.pm = s[96]; x.ddm = s[128];
+      const float4 v = ch.buf[(size_t)(b - b0) * 32 + lane];
+      BlockTerms x; x.p0 = v.x; x.p1 = v.y; x.pm = v.z;
+      x.dd = __shfl_sync(0xffffffffu, v.w, lane & ~3);
+      x.ddm = __shfl_sync(0xffffffffu, v.w, (lane & ~3) + 1);
       fold_block(f, x);
     }
   }
-  stream_blocks<Raw, D>(w, rb, bd, b1, a, t, [&](int, const BlockTerms& x) { fold_block(f, x); });
+  stream_blocks<Raw>(w, rb, bd, b1, a, lane, [&](int, const BlockTerms& x) { fold_block(f, x); });
   if (b1 < nb) {
     ch.mail_out[lane] = f.a0; ch.mail_out[32 + lane] = f.a1; ch.mail_out[64 + lane] = f.am;
     __threadfence_block();
@@ -584,9 +596,9 @@ __device__ __forceinline__ bool run_segment_typed(const DevMat w, int row, int b
 // KT = the one K-quant type of the launch (smaller kernel, no type switch in the loop), or 0 = decide per matrix
 template <int KT>
 __device__ __forceinline__ bool run_segment(const DevMat w, int row, int b0, int b1, const ActView& a, int lane, const Chain& ch, float& out) {
-  if (KT == GT_Q4_K || (KT == 0 && w.type == GT_Q4_K)) return run_segment_typed<RawQ4K, 4>(w, row, b0, b1, a, lane, ch, out);
-  if (KT == GT_Q6_K || (KT == 0 && w.type == GT_Q6_K)) return run_segment_typed<RawQ6K, 3>(w, row, b0, b1, a, lane, ch, out);
-  return run_segment_typed<RawQ5K, 3>(w, row, b0, b1, a, lane, ch, out);
+  if (KT == GT_Q4_K || (KT == 0 && w.type == GT_Q4_K)) return run_segment_typed<RawQ4K>(w, row, b0, b1, a, lane, ch, out);
+  if (KT == GT_Q6_K || (KT == 0 && w.type == GT_Q6_K)) return run_segment_typed<RawQ6K>(w, row, b0, b1, a, lane, ch, out);
+  return run_segment_typed<RawQ5K>(w, row, b0, b1, a, lane, ch, out);
 }
 
 // Q4_0: natural plane; lane l uses word (l & 3) of the block's 16 nibble bytes, low nibbles for l < 4 (elements 4l..4l+3),
@@ -758,14 +770,18 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
     }
   }
 
+  NormPre np;
+  preload_norm(np, p.norm_w, p.norm_b, p.norm_mode, p.K);
   pdl_wait();   // everything above touched only weights and shared memory; the input vector is the predecessor's output
-  stage_activation(p, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
+  stage_activation(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
   const ActView a = act_view(p.act, p.K, smem);
 
   if (kq) {
     if (s0 >= e0) return;
     Chain ch;
-    ch.buf = (float*)(smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15)) + (size_t)warp * MV_DEF_MAX * 160;
+    uint8_t* const dyn = smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15);
+    ch.def_max = p.def_max;
+    ch.buf = (float4*)dyn + (size_t)warp * p.def_max * 32;
     ch.mail_in = mailbox[warp]; ch.flag_in = &flags[warp];
     ch.mail_out = mailbox[warp + 1]; ch.flag_out = &flags[warp + 1];
     const int a0 = s0 % nb;
@@ -812,18 +828,25 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
 
 // host-side launch geometry shared by the engine and the op-level entry points
 struct MVLaunch { int grid; size_t smem; int kt; };
-inline MVLaunch matvec_launch_shape(const MVParams& p, int n_sm) {
+inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
   MVLaunch L;
   const size_t act = (act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15;
   const bool kq = type_is_kquant(p.seg[0].w.type);
   long units = 0;
   for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
   L.kt = 0;
+  p.def_max = 0;
   if (kq) {
     L.kt = p.seg[0].w.type;
     for (int s = 1; s < p.nseg; s++) if (p.seg[s].w.type != L.kt) L.kt = 0;
     L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm));
-    L.smem = act + (size_t)MV_WARPS * MV_DEF_MAX * 160 * 4;
+    const long room = (long)MV_SMEM_LIMIT - (long)act;
+    // a parked (mid-row) segment is never longer than a warp's range nor than a row; shared memory not asked for stays L1
+    const long nb = p.K / 256, tiles_per_cta = (units + L.grid - 1) / L.grid;
+    const long range = (tiles_per_cta * nb + MV_WARPS - 1) / MV_WARPS;
+    const long need = std::min<long>(range, nb - 1);
+    p.def_max = (int)std::max<long>(1, std::min<long>(std::min<long>(MV_DEF_MAX, need), room / (MV_WARPS * 512)));
+    L.smem = act + (size_t)MV_WARPS * p.def_max * 512;
   } else {
     L.grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)n_sm));
     L.smem = act;

@@ -93,7 +93,7 @@ void run_matvec(MVParams& p) {
   p.gelu_tab = tables().gelu;
   static bool attr = false;
   if (!attr) {
-    OPS_CUDA(matvec_set_smem_limit(200 * 1024));
+    OPS_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
     attr = true;
   }
   int n_sm = 148;
@@ -110,7 +110,9 @@ __global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const
   __shared__ double red[MV_WARPS];
   MVParams q{};
   q.x = x;
-  stage_activation(q, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
+  NormPre np;
+  preload_norm(np, nw, nb, mode, K);
+  stage_activation(q, np, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
   const size_t n = act_smem_bytes(act, K);
   for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
 }
@@ -121,7 +123,9 @@ __global__ void __launch_bounds__(MV_THREADS) k_gate_dump(const float* gate, con
   __shared__ double red[MV_WARPS];
   MVParams q{};
   q.x = gate; q.x2 = up; q.x_mode = 1; q.silu_tab = silu_tab;
-  stage_activation(q, nullptr, nullptr, nullptr, NORM_NONE, 0.f, M, ACT_F32, smem, red, false);
+  NormPre np;
+  preload_norm(np, nullptr, nullptr, NORM_NONE, M);
+  stage_activation(q, np, nullptr, nullptr, nullptr, NORM_NONE, 0.f, M, ACT_F32, smem, red, false);
   const float* f = (const float*)smem;
   for (int i = threadIdx.x; i < M; i += MV_THREADS) out[i] = f[i];
 }
