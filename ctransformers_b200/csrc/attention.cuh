@@ -187,7 +187,8 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   const int h = blockIdx.x, n = blockIdx.y, cg = blockIdx.z;
   const int hd = p.hd, per = hd >> 5;
   pdl_trigger();
-  pdl_wait();
+  // Everything up to pdl_wait() reads only what earlier steps left behind (device state, RoPE table, cached K/V rows of
+  // older positions): it overlaps the tail of the QKV kernel.  q/k/v of this token are read after the wait.
   const int pos = p.state[1] + n;
   if (pos >= p.n_ctx) return;
   const int T = pos + 1;
@@ -204,13 +205,34 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   uint16_t* k16 = q16 + hd;                             // [hd] f16 rotated key of this position, K-permuted order
   uint16_t* v16 = k16 + hd;                             // [hd] f16 value of this position, natural order
 
+  const int lim = min(T, n_vec);
+  const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
+  constexpr int CPW = ATTN_CH / ATTN_WARPS;             // V channels per warp
+  uint4 vpre[CPW][2];                                   // this warp's V rows, first two 256-position chunks
+  uint2 kpre[8];                                        // this warp's first 8 K rows (hd == 128)
+  float2 cs_pre = make_float2(1.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < CPW; j++)
+#pragma unroll
+    for (int ch = 0; ch < 2; ch++)
+      vpre[j][ch] = (ch * 256 < lim) ? *(const uint4*)(vhead + (size_t)(cg * ATTN_CH + warp + j * ATTN_WARPS) * cp + ch * 256 + lane * 8) : make_uint4(0, 0, 0, 0);
+  if (per == 4) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int t = min(warp * 8 + i, T - 1);
+      kpre[i] = (t == pos) ? make_uint2(0, 0) : *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
+    }
+  }
+  if (threadIdx.x < hd / 2) cs_pre = p.rope[(size_t)pos * (hd / 2) + threadIdx.x];
+  pdl_wait();
+
   {  // RoPE (pairs) + f16 conversion of q, k, v for this position
     const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
     const float* kv = p.k + (size_t)n * p.kv_stride + (size_t)kvh * hd;
     const float* vv = p.v + (size_t)n * p.kv_stride + (size_t)kvh * hd;
     uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kvh) * hd;
     for (int i = threadIdx.x; i < hd / 2; i += ATTN_THREADS) {
-      const float2 cs = p.rope[(size_t)pos * (hd / 2) + i];
+      const float2 cs = i == (int)threadIdx.x ? cs_pre : p.rope[(size_t)pos * (hd / 2) + i];
       const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
       float o0, o1;
       rope_pair(qv[i0], qv[i1], cs, p.neox, o0, o1);
@@ -237,7 +259,9 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         const int t = min(t0 + i, T - 1);
-        kk[i] = (t == pos) ? *(const uint2*)(k16 + lane * 4) : *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
+        if (t == pos) kk[i] = *(const uint2*)(k16 + lane * 4);
+        else if (t0 == warp * 8) kk[i] = kpre[i];
+        else kk[i] = *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
       }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -290,17 +314,20 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
   // leftover part (ggml.c:2415-2418): positions n_vec <= t < T are added one by one in double after the lane reduction.  They
   // are the row i_left of one 256-position chunk, i.e. element i_left of lanes 0..T-n_vec-1 of that chunk's 16-byte loads:
   // every lane forms its float product and the warp adds them in lane order through shuffles.
-  const int lim = min(T, n_vec);
   const int n_left = T - n_vec;                       // <= 31; <= 0 when the eval chunk extends past this token
   const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
-  const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
-  for (int cc = warp; cc < ATTN_CH; cc += ATTN_WARPS) {
+#pragma unroll
+  for (int j = 0; j < CPW; j++) {
+    const int cc = warp + j * ATTN_WARPS;
     const int c = cg * ATTN_CH + cc;
     const uint16_t* vrow = vhead + (size_t)c * cp;
     const uint16_t vcur = v16[c];
     float s = 0.f;
     for (int ch = 0; ch * 256 < lim; ch++) {
-      const uint4 vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
+      uint4 vv;
+      if (ch == 0) vv = vpre[j][0];
+      else if (ch == 1) vv = vpre[j][1];
+      else vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
       const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
       const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w}, pw[4] = {pp.x, pp.y, pp.z, pp.w};
 #pragma unroll
