@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one single-token decode pass of the whole hot path (160 weight mat-vecs + attention at a context of
+One "step" = one single-token decode pass of the whole hot path (129 mat-vec launches over 225 weight tensors + 32 attention launches at a context of
 256..511 tokens).  Workload: synthetic 7B-shaped model (random valid quant blocks in the reference's Q4_K_M tensor mix,
 3.8 GB of weights ≫ the 126 MB L2, so every step streams its inputs from HBM — no L2 flush needed), 256-token prompt
 prefilled untimed, then W warm-up + K timed decode steps.
@@ -12,7 +12,7 @@ prefilled untimed, then W warm-up + K timed decode steps.
             launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling)
   e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, logits D2H and the
             host sampler inside the timed region
-  roofline  dominant kernel k_matvec (HBM-bound): the GGUF bytes of the weights its 161 launches of a step read (4005.4 MB) ÷ their
+  roofline  dominant kernel k_matvec (HBM-bound): the GGUF bytes of the weights its 129 launches of a step read (4005.4 MB) ÷ their
             duration, measured live by replaying exactly those launches as a CUDA graph between CUDA events on the engine's
             stream; peak = MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes per launch (profiles/k_matvec_traffic.json).
             roofline.step = the same for the whole step (weights + KV + logits bytes ÷ device-timed step)

@@ -284,6 +284,7 @@ void Engine::launch_matvec(MVParams& p) {
   const MVLaunch L = matvec_launch_shape(p, sm_count_);
   CTB_CUDA(launch_matvec_kernel(L, stream_, p, pdl_));
   launches_per_step_++;
+  matvec_launches_++;
   mark(0);
 }
 
@@ -298,6 +299,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
   const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = hp_.n_head_kv, gqa = hp_.n_embd_gqa();
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
   launches_per_step_ = 0;
+  matvec_launches_ = 0;
   mark(-1);
   if (!matvec_only_) {
     k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
@@ -458,7 +460,7 @@ double Engine::time_matvec_only(int reps, long* launches) {
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
     cudaGraphDestroy(g);
   } catch (...) { stream_ = user; matvec_only_ = false; launches_per_step_ = keep; cudaStreamDestroy(cap); throw; }
-  if (launches) *launches = launches_per_step_;
+  if (launches) *launches = matvec_launches_;
   stream_ = user; matvec_only_ = false; launches_per_step_ = keep;
   cudaStreamDestroy(cap);
   cudaEvent_t e0, e1;

@@ -103,6 +103,7 @@ class Engine {
   void launch_attn(const struct AttnParams& ap);
   bool profiling_ = false;
   bool matvec_only_ = false;
+  long matvec_launches_ = 0;   // k_matvec launches of the step being enqueued
   bool pdl_ = true;            // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<int> prof_kind_;

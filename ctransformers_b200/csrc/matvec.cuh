@@ -24,7 +24,10 @@
 
 namespace ctb {
 
-constexpr int MV_THREADS = 512;    // one persistent CTA per SM (<= 128 registers per thread): the activation prologue is paid once per SM
+#ifndef CTB_THREADS
+#define CTB_THREADS 512
+#endif
+constexpr int MV_THREADS = CTB_THREADS;    // one persistent CTA per SM (<= 128 registers per thread): the activation prologue is paid once per SM
 constexpr int MV_WARPS = MV_THREADS / 32;
 constexpr int MV_ROWS = 4;   // Q4_0 / Q8_0: rows per warp (one per 8-lane group, in-lane chain)
 constexpr int MV_MAX_SEG = 3;
@@ -507,7 +510,7 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 
 // Hand-off of a row tile's fold state between consecutive warps of a CTA (see k_matvec): warp w receives at most one state
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
-constexpr int MV_SMEM_LIMIT = 220 * 1024;   // dynamic shared memory a launch may ask for (227 KB per CTA minus the static part)
+constexpr int MV_SMEM_LIMIT = 227 * 1024 - ((MV_WARPS + 1) * 388 + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
 constexpr int MV_DEF_MAX = 12;   // most blocks of a mid-row segment whose terms are parked before the state arrives
 constexpr int MV_RING = 2;       // blocks per lane in flight in the register pipeline (measured: 2 > 3 > 1 > 4 once L2 is prefetched)   // most blocks of a mid-row segment whose terms are parked before the state arrives
 struct Chain {

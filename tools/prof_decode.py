@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Workload for ncu: bench.py's model, a short prompt, then a few single-token decode steps.
 
-    ncu -k regex:'k_matvec|k_attn' --launch-skip $((NP*193)) -c 193 ... python tools/prof_decode.py NP NSTEPS
+    ncu -k regex:'k_matvec|k_attn|k_embed' --launch-skip $((NP*161+1)) -c 162 ... python tools/prof_decode.py NP NSTEPS
 
-(7B shape: 161 k_matvec + 32 k_attn launches per token.)  Never a source of bench numbers.
+(7B shape, per token: 1 k_embed + 32 x (4 k_matvec + 1 k_attn) = 161 launches, + 1 k_matvec for the logits of the last
+prompt token and of every decode step.)  Never a source of bench numbers.
 """
 import sys
 from pathlib import Path
