@@ -171,11 +171,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    dist = None
+    from ctransformers_b200 import replicas
+    who = replicas.Rank.from_env()
+    rank, world, local = who.rank, who.world, who.local
     if args.impl == "reference":
+        if not replicas.reference_rank_runs(who):
+            return                       # under torchrun only rank 0 times the CPU reference
         return run_reference(args, rank, world, lambda: None)
 
     import numpy as np
@@ -183,22 +184,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist_mod
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
-        dist = dist_mod
+    group = replicas.Group(who, backend="nccl", device=f"cuda:{local}")
 
     def barrier():
-        if dist:
-            dist.barrier()
-        torch.cuda.synchronize()
+        group.barrier(torch.cuda.synchronize)
 
-    def max_over_ranks(x):
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    max_over_ranks = group.max
 
     from ctransformers_b200 import AutoModelForCausalLM, synth
     path = ensure_model(rank, world, barrier)
@@ -226,7 +217,8 @@ def main():
     assert ms > 0
     ms = max_over_ranks(ms)
     tokens_dev = list(out[:steps])
-    value = world * steps / (ms / 1e3)
+    replicas_agree = all(t == tokens_dev for t in group.gather_ints(tokens_dev))   # every replica decodes the same sequence
+    value = replicas.aggregate_tokens_per_s(world, steps, ms)
 
     # ------------------------------------------------------------------ end to end through the public API ("e2e")
     tok = prefill()
@@ -241,7 +233,7 @@ def main():
         e2e_tokens.append(tok)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = world * steps / e2e_s
+    e2e = replicas.aggregate_tokens_per_s(world, steps, e2e_s * 1e3)
 
     # ------------------------------------------------------------------ roofline
     peak, peak_src = hbm_peak()
@@ -286,7 +278,7 @@ def main():
                 "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs"},
         "gpu_launches": int(llm.ctb_llm_launches_per_token()) * steps,
         "roofline": roofline,
-        "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps],
+        "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps], "replicas_agree": replicas_agree,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and REF_SO.exists():
@@ -306,8 +298,7 @@ def main():
                                   "sample": f"{n_dec} decode steps after a {n_prompt}-token prompt (context ≈{n_prompt + 2 * len(sweep) + n_dec}), same model file, unmodified reference CPU build (AVX2), {threads} threads (best of the sweep)"}
     if rank == 0:
         print(json.dumps(result))
-    if dist:
-        dist.destroy_process_group()
+    group.close()
 
 
 if __name__ == "__main__":

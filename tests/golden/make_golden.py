@@ -56,8 +56,10 @@ def ref_llm(path, ctx):
     return AutoModelForCausalLM.from_pretrained(str(path), lib=str(refs.REF_SO), context_length=ctx, threads=4)
 
 
-def models(tmp):
+def models(tmp, only=None):
     for name in modelcases.CASES:
+        if only and name not in only:
+            continue
         path, ctx = modelcases.build(name, tmp)
         llm = ref_llm(path, ctx)
         prompt = modelcases.prompt_for(name)
@@ -104,8 +106,13 @@ def host_logic(tmp):
 
 if __name__ == "__main__":
     assert refs.have_ref(), "build oracle/_ref first: make -C oracle ref"
+    import sys
+    only = sys.argv[1:]          # python make_golden.py [model case ...]: regenerate only those model fixtures
     with tempfile.TemporaryDirectory() as tmp:
-        kat_quant()
-        models(tmp)
-        host_logic(tmp)
+        if only:
+            models(tmp, only)
+        else:
+            kat_quant()
+            models(tmp)
+            host_logic(tmp)
     print("golden vectors written to", HERE)

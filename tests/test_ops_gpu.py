@@ -82,6 +82,22 @@ def test_mul_mat_vs_oracle(lib, t, k, m):
     _same_bits(got, want)
 
 
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K])
+@pytest.mark.parametrize("k,m", [(4096, 4096 + 37), (4096, 22016), (11008, 4096), (2048, 1184 + 8), (256, 9000)])
+def test_mul_mat_full_size_partitions(lib, t, k, m):
+    """Bench-sized shapes: many row tiles per CTA, warp ranges that start and end in the middle of a row (fold state handed from
+    warp to warp, parked terms), ranges longer and shorter than a row, a ragged last tile — all bit-exact with the oracle."""
+    o = refs.oracle()
+    rng = np.random.default_rng(t * 77 + k + m)
+    w = _rand_weights(t, k, m, seed=t + k + m)
+    x = _act(rng, k)[None, :]
+    want = np.zeros((1, m), np.float32)
+    got = np.zeros((1, m), np.float32)
+    assert o.orc_mul_mat(t, ptr(w), ptr(x), ptr(want), k, m, 1) == 0
+    assert lib.ctb_mul_mat(t, ptr(w), ptr(x), ptr(got), k, m, 1) == 0
+    _same_bits(got, want)
+
+
 @pytest.mark.parametrize("k", [512, 1000])
 def test_mul_mat_f16_weights(lib, k):
     """F16 weights take ggml_vec_dot_f16 with the activation row rounded to f16 (ggml.c:1665-1675, 2392-2426)."""
