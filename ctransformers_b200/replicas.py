@@ -4,7 +4,9 @@ Batch-1 decode is a single dependent chain, so N GPUs run N ind
 is the rendezvous, a barrier around the timed region and a MAX reduction of the per-rank device time.  `torch.distributed`
 does that: backend "nccl" on GPUs, "gloo" in the CPU tests.
 """
+import contextlib
 import os
+import sys
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Sequence
 
@@ -20,6 +22,21 @@ class Rank:
         return cls(int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0)))
 
 
+@contextlib.contextmanager
+def _stdout_to_stderr():
+    """NCCL prints its version banner on file descriptor 1 when the first communicator is created; bench.py's stdout must
+    carry exactly one JSON line, so the banner is sent to stderr."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    try:
+        os.dup2(2, 1)
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 class Group:
     """Barrier / max-over-ranks / gather on top of torch.distributed; a no-op group when world == 1."""
 
@@ -30,9 +47,11 @@ class Group:
             import torch.distributed as dist
             backend = backend or ("nccl" if self.device.startswith("cuda") else "gloo")
             kw = {"device_id": torch.device(self.device)} if backend == "nccl" else {}
-            if not dist.is_initialized():
-                dist.init_process_group(backend, rank=who.rank, world_size=who.world, **kw)
-            self.dist = dist
+            with _stdout_to_stderr():
+                if not dist.is_initialized():
+                    dist.init_process_group(backend, rank=who.rank, world_size=who.world, **kw)
+                self.dist = dist
+                self.barrier()                 # creates the communicator now, while stdout is diverted
 
     def barrier(self, sync: Optional[Callable[[], None]] = None) -> None:
         if self.dist:
