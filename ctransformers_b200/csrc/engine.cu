@@ -278,7 +278,8 @@ void Engine::launch_attn(const AttnParams& ap) {
   CTB_CUDA(cudaLaunchKernelEx(&cfg, k_attn, ap));
 }
 
-void Engine::launch_matvec(MVParams& p) {
+void Engine::launch_matvec(MVParams& p, int kind) {
+  if (matvec_only_ && !((matvec_mask_ >> kind) & 1)) return;
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
   const MVLaunch L = matvec_launch_shape(p, sm_count_);
@@ -329,7 +330,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
           p.act = act_format_for(ws[i]->type); p.nseg = 0;
           for (int j = i; j < 3; j++)
             if (!done[j] && act_format_for(ws[j]->type) == p.act) { p.seg[p.nseg++] = seg(*ws[j], outs[j]); done[j] = true; }
-          launch_matvec(p);
+          launch_matvec(p, MVK_QKV);
         }
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
@@ -340,20 +341,20 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
         p.seg[0] = seg(L.wo, y, EPI_ADD, x);
-        launch_matvec(p);
+        launch_matvec(p, MVK_WO);
       }
       {  // ffn_norm + gate and up projections as two independent row sets (SiLU·mul is applied by the consumer's prologue)
         MVParams p{};
         p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
         p.act = act_format_for(L.w1.type); p.nseg = 2;
         p.seg[0] = seg(L.w1, ffn_); p.seg[1] = seg(L.w3, ffn2_);
-        launch_matvec(p);
+        launch_matvec(p, MVK_UP);
       }
       {  // w2 on silu(gate)*up, + residual
         MVParams p{};
         p.x = ffn_; p.x2 = ffn2_; p.x_mode = 1; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, x, EPI_ADD, y);
-        launch_matvec(p);
+        launch_matvec(p, MVK_DOWN);
       }
       // x now holds the next layer's input
     } else {
@@ -368,14 +369,14 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.act = act_format_for(L.wqkv.type); p.nseg = 1;
         p.seg[0] = seg(L.wqkv, qkv_);
         if (fuse) { p.seg[1] = seg(L.w3, ffn_); p.nseg = 2; }   // GELU is applied by ffn_down's prologue
-        launch_matvec(p);
+        launch_matvec(p, MVK_QKV);
       }
       if (!fuse) {
         MVParams p{};
         p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd; p.norm_w = L.attn_norm; p.norm_b = L.attn_norm_b;
         p.act = act_format_for(L.w3.type); p.nseg = 1;
         p.seg[0] = seg(L.w3, ffn_);
-        launch_matvec(p);
+        launch_matvec(p, MVK_UP);
       }
       ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
       if (!matvec_only_) launch_attn(ap);
@@ -385,13 +386,13 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
         p.seg[0] = seg(L.wo, attn_o_);
-        launch_matvec(p);
+        launch_matvec(p, MVK_WO);
       }
       {  // ffn_down, then + attn_out, then + layer input (llama.cpp:2767-2771 order)
         MVParams p{};
         p.x = ffn_; p.x_mode = 2; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, y, EPI_ADD2, attn_o_, x);
-        launch_matvec(p);
+        launch_matvec(p, MVK_DOWN);
       }
       std::swap(x, y);
     }
@@ -401,7 +402,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
     p.x = x; p.norm_w = out_norm_; p.norm_b = out_norm_b_; p.norm_mode = hp_.falcon ? NORM_LAYER : NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
     p.norm_out = d_embd_; p.act = act_format_for(output_.type); p.nseg = 1;
     p.seg[0] = seg(output_, d_logits_);
-    launch_matvec(p);
+    launch_matvec(p, MVK_OUT);
     if (greedy && !matvec_only_) {
       k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
       k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
@@ -445,7 +446,8 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
 
 // The step's mat-vec launches alone (same kernels, same parameters, same order, no attention / embedding / argmax), replayed
 // as a CUDA graph: their summed duration under in-graph launch conditions is what bench.py's roofline for k_matvec uses.
-double Engine::time_matvec_only(int reps, long* launches) {
+double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
+  matvec_mask_ = mask ? mask : ~0u;
   CTB_CUDA(cudaSetDevice(device_));
   cudaStream_t user = stream_, cap;
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));

@@ -49,7 +49,7 @@ class Engine {
   double decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens);
   // One eager (un-graphed) decode step at n_past with a CUDA event after every kernel; accumulates the
   // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
-  double time_matvec_only(int reps, long* launches);
+  double time_matvec_only(int reps, long* launches, unsigned mask = 0);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
 
   float* logits() { return h_logits_; }
@@ -99,10 +99,12 @@ class Engine {
   void enqueue_step(bool with_logits, bool greedy);
   void build_graphs();
   void destroy_graphs();
-  void launch_matvec(struct MVParams& p);
+  enum : int { MVK_QKV = 0, MVK_WO = 1, MVK_UP = 2, MVK_DOWN = 3, MVK_OUT = 4 };   // which projection a mat-vec launch is
+  void launch_matvec(struct MVParams& p, int kind);
   void launch_attn(const struct AttnParams& ap);
   bool profiling_ = false;
   bool matvec_only_ = false;
+  unsigned matvec_mask_ = ~0u;  // time_matvec_only: bit k set = launches of kind k are kept
   long matvec_launches_ = 0;   // k_matvec launches of the step being enqueued
   bool pdl_ = true;            // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
   std::vector<cudaEvent_t> prof_ev_;

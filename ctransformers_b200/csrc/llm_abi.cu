@@ -196,9 +196,11 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
   }
 }
 
-double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches) {
+double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches) { return ctb_llm_time_matvec_kinds(llm, reps, launches, 0); }
+
+double ctb_llm_time_matvec_kinds(LLM* llm, int reps, long* launches, unsigned kind_mask) {
   try {
-    return llm->engine->time_matvec_only(reps < 1 ? 1 : reps, launches);
+    return llm->engine->time_matvec_only(reps < 1 ? 1 : reps, launches, kind_mask);
   } catch (const std::exception& e) {
     fprintf(stderr, "ctransformers-b200: time_matvec_only failed: %s\n", e.what());
     return -1.0;

@@ -24,6 +24,10 @@
 
 namespace ctb {
 
+#ifndef CTB_PF
+#define CTB_PF 2     // L2 prefetch policy: 0 none, 1 the warp's whole range before the prologue, 2 rolling, CTB_PFD blocks ahead (measured best)
+#define CTB_PFD 4
+#endif
 #ifndef CTB_THREADS
 #define CTB_THREADS 512
 #endif
@@ -165,6 +169,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     double ss = 0.0;
     for (int ps = 0; ps < passes; ps++) {
       const int base = (ps * MV_THREADS + t) * 16;
+      if ((base & ~511) >= K) continue;     // the whole warp lies past the end of x (warp-uniform): nothing to add
       float v[16];
       if (ps == 0) {
 #pragma unroll
@@ -180,6 +185,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     double s1 = 0.0;
     for (int ps = 0; ps < passes; ps++) {
       const int base = (ps * MV_THREADS + t) * 16;
+      if ((base & ~511) >= K) continue;
       float v[16];
       load16x(xs, base, K - base, v);
 #pragma unroll
@@ -190,6 +196,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     double s2 = 0.0;
     for (int ps = 0; ps < passes; ps++) {
       const int base = (ps * MV_THREADS + t) * 16;
+      if ((base & ~511) >= K) continue;
       float v[16];
       load16x(xs, base, K - base, v);
 #pragma unroll
@@ -207,6 +214,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
   for (int ps = 0; ps < passes; ps++) {
     const int base = (ps * MV_THREADS + t) * 16;
     const int valid = K - base;
+    if ((base & ~511) >= K) continue;       // warp-uniform: this warp has no elements in this pass
     float v[16];
     if (ps == 0) {
 #pragma unroll
@@ -512,7 +520,10 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
 constexpr int MV_SMEM_LIMIT = 227 * 1024 - ((MV_WARPS + 1) * 388 + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
 constexpr int MV_DEF_MAX = 12;   // most blocks of a mid-row segment whose terms are parked before the state arrives
-constexpr int MV_RING = 2;       // blocks per lane in flight in the register pipeline (measured: 2 > 3 > 1 > 4 once L2 is prefetched)   // most blocks of a mid-row segment whose terms are parked before the state arrives
+#ifndef CTB_RING
+#define CTB_RING 2
+#endif
+constexpr int MV_RING = CTB_RING;     // blocks per lane in flight in the register pipeline (measured: 2 > 3 > 1 > 4 once L2 is prefetched)   // most blocks of a mid-row segment whose terms are parked before the state arrives
 struct Chain {
   float4* buf;                   // warp-private [def_max][32] parked block terms
   int def_max;
@@ -543,14 +554,25 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
   Raw ring[D];
   const int last = b1 - 1;
 #pragma unroll
-  for (int i = 0; i < D; i++) load_raw(ring[i], w, rb + min(b0 + i, last), t);   // tail slots re-load the last block (a cache hit)
+#ifdef CTB_FAKE_LOADS
+#define CTB_BLK(x) ((size_t)((x) & 7))
+#else
+#define CTB_BLK(x) (x)
+#endif
+  for (int i = 0; i < D; i++) load_raw(ring[i], w, CTB_BLK(rb + min(b0 + i, last)), t);   // tail slots re-load the last block (a cache hit)
   for (int b = b0; b < b1; b += D) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
       CTB_PIN();
+#if CTB_PF == 2
+      if (b + i + CTB_PFD < b1 && ((b + i) & 3) == t) {   // rolling L2 prefetch: the row's block CTB_PFD ahead, one lane of four per block
+        prefetch_l2(w.qs + (rb + b + i + CTB_PFD) * 128);
+        if (((b + i) & 7) < 4) prefetch_l2(w.sc + (rb + b + i + CTB_PFD) * 16);
+      }
+#endif
       if (b + i < b1) sink(b + i, block_terms(ring[i], b + i, a, t));
       CTB_PIN();
-      load_raw(ring[i], w, rb + min(b + i + D, last), t);
+      load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
     }
   }
 }
@@ -768,7 +790,11 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
       const int s = ts.locate(tile);
       const DevMat& w = p.seg[s].w;
       const int row = min(tile * MV_KQ_ROWS + (lane >> 2), w.M - 1);
+#if CTB_PF == 1
       prefetch_row(w, (size_t)row * nb, b0, b0 + len, lane & 3);
+#elif CTB_PF == 2
+      prefetch_row(w, (size_t)row * nb, b0, min(b0 + len, b0 + CTB_PFD), lane & 3);
+#endif
       pos += len;
     }
   }

@@ -73,6 +73,9 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
  * out), replayed reps times as a CUDA graph between two CUDA events: returns milliseconds per step, < 0 on error;
  * *launches = mat-vec launches per step.  KV cache and logits are not meaningful afterwards. */
 double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches);
+/* Same, restricted to the launches whose kind bit is set in kind_mask (bit 0 QKV, 1 attention output, 2 FFN gate+up,
+ * 3 FFN down, 4 output head; 0 = all): per-projection timing under in-graph launch conditions. */
+double ctb_llm_time_matvec_kinds(LLM* llm, int reps, long* launches, unsigned kind_mask);
 
 /* Host-only pieces of the boundary, callable without a GPU: the GGUF vocabulary with its SPM / BPE tokenizer
  * (llama.cpp:1648-1760, 3080-3427, 6151-6187) and the sampler chain of llama_llm::Sample (llama.cc:53-84). */

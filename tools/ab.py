@@ -23,5 +23,11 @@ for spec in sys.argv[1:]:
         best = min(best, ms / 64)
     n = C.c_long(0)
     mv = llm.ctb_llm_time_matvec_only(32, C.byref(n))
+    kinds = []
+    if hasattr(llm, "ctb_llm_time_matvec_kinds"):
+        for k, nm in enumerate(["qkv", "wo", "up", "down", "out"]):
+            ms_k = llm.ctb_llm_time_matvec_kinds(16, C.byref(n), 1 << k)
+            kinds.append(f"{nm} {1e3 * ms_k / max(1, n.value):.2f}us x{n.value}")
+    print("   per launch, same-kind launches back to back:", ", ".join(kinds))
     print(f"{name}: {1e3 / best:.1f} tok/s  step {best:.4f} ms  matvec-only {mv:.4f} ms/step  first tokens {list(out[:4])}", flush=True)
     del llm
