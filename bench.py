@@ -275,7 +275,8 @@ def main():
         "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": shape.n_vocab * 4 + shape.n_embd * 4,
-                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs"},
+                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs",
+                "lookahead_hits": int(llm.ctb_llm_speculative_hits())},
         "gpu_launches": int(llm.ctb_llm_launches_per_token()) * steps,
         "roofline": roofline,
         "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps], "replicas_agree": replicas_agree,

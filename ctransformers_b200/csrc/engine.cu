@@ -240,6 +240,9 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   memset(h_embd_, 0, (size_t)hp_.n_embd * 4);
 
   if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
+  if (const char* e = getenv("CTB_NO_SPEC")) spec_on_ = !(e[0] == '1');
+  CTB_CUDA(cudaMallocHost(&h_spec_tok_, 16));
+  CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
   CTB_CUDA(cudaDeviceSynchronize());
@@ -256,6 +259,8 @@ Engine::~Engine() {
   if (h_tokens_out_) cudaFreeHost(h_tokens_out_);
   if (d_tokens_out_) cudaFree(d_tokens_out_);
   if (arena_) cudaFree(arena_);
+  if (h_spec_tok_) cudaFreeHost(h_spec_tok_);
+  if (ev_pick_) cudaEventDestroy(ev_pick_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
@@ -423,6 +428,7 @@ void Engine::mark(int kind) {
 
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
   CTB_CUDA(cudaSetDevice(device_));
+  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
@@ -448,6 +454,7 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
 // as a CUDA graph: their summed duration under in-graph launch conditions is what bench.py's roofline for k_matvec uses.
 double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   matvec_mask_ = mask ? mask : ~0u;
+  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   CTB_CUDA(cudaSetDevice(device_));
   cudaStream_t user = stream_, cap;
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -520,6 +527,25 @@ void Engine::build_graphs() {
   cudaStreamDestroy(cap);
 }
 
+// After an eval: pick the greedy next token on the device and — once the caller has proven to decode greedily (its last
+// tokens were exactly those picks) — run the step for that token right away, while the host is still sampling and crossing
+// the FFI.  The next eval() that asks for exactly this token at this position only has to fetch the result; any other request
+// simply runs after it (stream order) and overwrites the same KV slot, so a wrong guess costs time, never correctness.
+void Engine::after_eval(int next_pos) {
+  spec_pending_ = false;
+  spec_pos_ = -1;
+  if (!spec_on_ || next_pos >= hp_.n_ctx) return;
+  k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
+  k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
+  CTB_CUDA(cudaMemcpyAsync(h_spec_tok_, d_state_, 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaEventRecord(ev_pick_, stream_));
+  spec_pos_ = next_pos;
+  if (spec_streak_ >= 2) {
+    CTB_CUDA(cudaGraphLaunch(graph_full_, stream_));
+    spec_pending_ = true;
+  }
+}
+
 void Engine::eval(const int* tokens, int n, int n_past) {
   if (n <= 0) return;
   CTB_CUDA(cudaSetDevice(device_));
@@ -528,24 +554,42 @@ void Engine::eval(const int* tokens, int n, int n_past) {
     h_state_cap_ = std::max(n, 512);
     CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16));
   }
-  CTB_CUDA(cudaEventRecord(ev0_, stream_));
-  for (int i = 0; i < n; i++) {
-    int* st = h_state_ + (size_t)i * 4;
-    st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = n_past + n;   // n_total: row length of this eval's attention mat-muls
-    CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
-    CTB_CUDA(cudaGraphLaunch(i == n - 1 ? graph_full_ : graph_nolog_, stream_));
+  bool hit = false;
+  if (spec_pos_ >= 0) {
+    const bool was_pending = spec_pending_;
+    bool guessed = false;
+    if (n == 1 && n_past == spec_pos_) {
+      CTB_CUDA(cudaEventSynchronize(ev_pick_));
+      guessed = *h_spec_tok_ == tokens[0];
+    }
+    spec_streak_ = guessed ? spec_streak_ + 1 : 0;
+    hit = guessed && was_pending;
+    spec_pending_ = false;
+    spec_pos_ = -1;
   }
+  CTB_CUDA(cudaEventRecord(ev0_, stream_));
+  if (!hit) {
+    for (int i = 0; i < n; i++) {
+      int* st = h_state_ + (size_t)i * 4;
+      st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = n_past + n;   // n_total: row length of this eval's attention mat-muls
+      CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
+      CTB_CUDA(cudaGraphLaunch(i == n - 1 ? graph_full_ : graph_nolog_, stream_));
+    }
+  }   // else: the step for this token at this position is already in the stream
   CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaEventRecord(ev1_, stream_));
-  CTB_CUDA(cudaStreamSynchronize(stream_));
+  after_eval(n_past + n);
+  CTB_CUDA(cudaEventSynchronize(ev1_));
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0_, ev1_);
   stats.last_eval_ms = ms;
+  stats.spec_hits += hit ? 1 : 0;
 }
 
 double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens) {
   if (n_steps <= 0) return 0.0;
+  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (n_steps > tokens_out_cap_) throw std::runtime_error("decode_greedy: too many steps");
   if (n_past + n_steps > hp_.n_ctx) throw std::runtime_error("decode_greedy: would run past the context length");
   CTB_CUDA(cudaSetDevice(device_));

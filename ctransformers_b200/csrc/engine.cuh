@@ -33,7 +33,7 @@ struct LayerW {
   const float* ffn_norm = nullptr;
 };
 
-struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; };
+struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; long spec_hits = 0; };
 
 class Engine {
  public:
@@ -90,7 +90,12 @@ class Engine {
   int tokens_out_cap_ = 0;
 
   cudaGraphExec_t graph_full_ = nullptr, graph_nolog_ = nullptr, graph_greedy_ = nullptr;
-  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_pick_ = nullptr;
+  // speculative next step (see after_eval)
+  bool spec_on_ = true, spec_pending_ = false;
+  int spec_pos_ = -1, spec_streak_ = 0;
+  int* h_spec_tok_ = nullptr;
+  void after_eval(int next_pos);
   int sm_count_ = 148;
   long launches_per_step_ = 0;
 

@@ -28,6 +28,9 @@ namespace ctb {
 #define CTB_PF 2     // L2 prefetch policy: 0 none, 1 the warp's whole range before the prologue, 2 rolling, CTB_PFD blocks ahead (measured best)
 #define CTB_PFD 4
 #endif
+#ifndef CTB_LPR
+#define CTB_LPR 4     // K-quants: GPU lanes per weight row (each plays 8/CTB_LPR of the reference kernel's 8 AVX lanes)
+#endif
 #ifndef CTB_THREADS
 #define CTB_THREADS 512
 #endif
@@ -352,125 +355,135 @@ __device__ __forceinline__ int scale_fold(const int (&dp)[8], uint32_t sc03, uin
   return s;
 }
 
-struct ActBlock { int4 a[2][2]; float yd; };   // a[e][h]: activation words of AVX lane (e ? t+4 : t), sub-blocks 4h..4h+3
-__device__ __forceinline__ ActBlock load_act_block(const ActView& a, int b, int t) {
-  ActBlock r;
-  const int8_t* base = a.qs + (size_t)b * 256;
-  r.a[0][0] = *(const int4*)(base + t * 16);
-  r.a[1][0] = *(const int4*)(base + (t + 4) * 16);
-  r.a[0][1] = *(const int4*)(base + 128 + t * 16);
-  r.a[1][1] = *(const int4*)(base + 128 + (t + 4) * 16);
-  r.yd = a.d[b];
-  return r;
+constexpr int KQ_LPR = CTB_LPR;            // lanes per row
+constexpr int KQ_NA = 8 / KQ_LPR;          // AVX lanes per GPU lane: lane u of a row plays l = u + KQ_LPR*e, e = 0..KQ_NA-1
+constexpr int KQ_NM = KQ_LPR >= 4 ? 1 : 4 / KQ_LPR;   // Q4_K mins lanes per GPU lane: k = u + KQ_LPR*i
+static_assert(KQ_LPR == 4 || KQ_LPR == 2, "lanes per row: 4 or 2");
+
+// activation words of AVX lane l of block b: sub-blocks 0..3 and 4..7
+__device__ __forceinline__ void load_act_lane(const ActView& a, int b, int l, int (&av)[8]) {
+  const int8_t* base = a.qs + (size_t)b * 256 + l * 16;
+  const int4 lo = *(const int4*)base, hi = *(const int4*)(base + 128);
+  av[0] = lo.x; av[1] = lo.y; av[2] = lo.z; av[3] = lo.w; av[4] = hi.x; av[5] = hi.y; av[6] = hi.z; av[7] = hi.w;
 }
 
-// What one block contributes to one row, for this lane's two AVX lanes: p0/p1 = (float)sumi of lanes t / t+4, dd = y.d·d,
-// and the mins term pm·ddm (Q4_K: mins lane k = t; Q5_K: the scalar term, lane t == 0; Q6_K: none).
-struct BlockTerms { float p0, p1, dd, pm, ddm; };
+// What one block contributes to one row, for this lane's AVX lanes: p[e] = (float)sumi of lane l_e, dd = y.d·d, and the mins
+// terms pm[i]·ddm (Q4_K: mins lanes k = u + KQ_LPR*i; Q5_K: the scalar term in pm[0] of lane u == 0; Q6_K: none).
+struct BlockTerms { float p[KQ_NA]; float pm[KQ_NM]; float dd, ddm; };
 
 // Raw block data of one lane, held in registers by the software pipeline below
-struct RawQ4K { int4 c0, c1, ch; };
-struct RawQ5K { int4 c0, c1, ch; uint32_t hb0, hb1; };
-struct RawQ6K { int4 ql0, ql1, scv; int2 qh0, qh1; uint16_t d; };
-__device__ __forceinline__ void load_raw(RawQ4K& r, const DevMat& w, size_t blk, int t) {
-  r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
+struct RawQ4K { int4 c[KQ_NA]; int4 ch; };
+struct RawQ5K { int4 c[KQ_NA]; int4 ch; uint32_t hb[KQ_NA]; };
+struct RawQ6K { int4 ql[KQ_NA]; int2 qh[KQ_NA]; int4 scv; uint16_t d; };
+__device__ __forceinline__ void load_raw(RawQ4K& r, const DevMat& w, size_t blk, int u) {
+#pragma unroll
+  for (int e = 0; e < KQ_NA; e++) r.c[e] = ldg_stream16(w.qs + blk * 128 + (u + KQ_LPR * e) * 16);
   r.ch = ldg_keep16(w.sc + blk * 16);
 }
-__device__ __forceinline__ void load_raw(RawQ5K& r, const DevMat& w, size_t blk, int t) {
-  r.c0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.c1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
+__device__ __forceinline__ void load_raw(RawQ5K& r, const DevMat& w, size_t blk, int u) {
+#pragma unroll
+  for (int e = 0; e < KQ_NA; e++) {
+    r.c[e] = ldg_stream16(w.qs + blk * 128 + (u + KQ_LPR * e) * 16);
+    r.hb[e] = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + (u + KQ_LPR * e) * 4));
+  }
   r.ch = ldg_keep16(w.sc + blk * 16);
-  r.hb0 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + t * 4)); r.hb1 = (uint32_t)__ldg((const int*)(w.qh + blk * 32 + 16 + t * 4));
 }
-__device__ __forceinline__ void load_raw(RawQ6K& r, const DevMat& w, size_t blk, int t) {
-  r.ql0 = ldg_stream16(w.qs + blk * 128 + t * 16); r.ql1 = ldg_stream16(w.qs + blk * 128 + 64 + t * 16);
-  r.qh0 = ldg_stream8(w.qh + blk * 64 + t * 8); r.qh1 = ldg_stream8(w.qh + blk * 64 + 32 + t * 8);
+__device__ __forceinline__ void load_raw(RawQ6K& r, const DevMat& w, size_t blk, int u) {
+#pragma unroll
+  for (int e = 0; e < KQ_NA; e++) {
+    r.ql[e] = ldg_stream16(w.qs + blk * 128 + (u + KQ_LPR * e) * 16);
+    r.qh[e] = ldg_stream8(w.qh + blk * 64 + (u + KQ_LPR * e) * 8);
+  }
   r.scv = ldg_keep16(w.sc + blk * 16);
   r.d = __ldg(w.d + blk);
 }
 
 // k_quants.c:2651-2714
-__device__ __forceinline__ BlockTerms block_terms(const RawQ4K& raw, int b, const ActView& a, int t) {
-  const int4 c0 = raw.c0, c1 = raw.c1, ch = raw.ch;
-  const ActBlock ab = load_act_block(a, b, t);
+__device__ __forceinline__ BlockTerms block_terms(const RawQ4K& raw, int b, const ActView& a, int u) {
+  const int4 ch = raw.ch;
   uint32_t sc03, sc47, m03, m47;
   unpack_k4((uint32_t)ch.y, (uint32_t)ch.z, (uint32_t)ch.w, sc03, sc47, m03, m47);
-  float pv[2];
+  BlockTerms r;
+  const float yd = a.d[b];
 #pragma unroll
-  for (int e = 0; e < 2; e++) {
-    const int4 q = e ? c1 : c0;
+  for (int e = 0; e < KQ_NA; e++) {
+    const int4 q = raw.c[e];
     const uint32_t qv[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
+    int av[8];
+    load_act_lane(a, b, u + KQ_LPR * e, av);
     int dp[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       dp[2 * j] = __dp4a((int)(qv[j] & 0x0f0f0f0fu), av[2 * j], 0);
       dp[2 * j + 1] = __dp4a((int)((qv[j] >> 4) & 0x0f0f0f0fu), av[2 * j + 1], 0);
     }
-    pv[e] = (float)scale_fold(dp, sc03, sc47);
+    r.p[e] = (float)scale_fold(dp, sc03, sc47);
   }
-  BlockTerms r;
-  r.p0 = pv[0]; r.p1 = pv[1];
-  r.dd = __fmul_rn(ab.yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
-  // mins lane k = t: m[2k]*(bsums[4k]+bsums[4k+1]) + m[2k+1]*(bsums[4k+2]+bsums[4k+3])
-  const int2 bsv = *(const int2*)(a.bs + b * 16 + 4 * t);
-  const int s0 = (int)(short)(bsv.x & 0xffff) + (int)(short)((uint32_t)bsv.x >> 16);
-  const int s1 = (int)(short)(bsv.y & 0xffff) + (int)(short)((uint32_t)bsv.y >> 16);
-  const uint32_t mw = (t < 2 ? m03 : m47) >> ((t & 1) * 16);
-  r.pm = (float)((int)(mw & 0xffu) * s0 + (int)((mw >> 8) & 0xffu) * s1);
-  r.ddm = __fmul_rn(-ab.yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
+  r.dd = __fmul_rn(yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
+  // mins lane k: m[2k]*(bsums[4k]+bsums[4k+1]) + m[2k+1]*(bsums[4k+2]+bsums[4k+3])
+#pragma unroll
+  for (int i = 0; i < KQ_NM; i++) {
+    const int k = u + KQ_LPR * i;
+    const int2 bsv = *(const int2*)(a.bs + b * 16 + 4 * k);
+    const int s0 = (int)(short)(bsv.x & 0xffff) + (int)(short)((uint32_t)bsv.x >> 16);
+    const int s1 = (int)(short)(bsv.y & 0xffff) + (int)(short)((uint32_t)bsv.y >> 16);
+    const uint32_t mw = (k < 2 ? m03 : m47) >> ((k & 1) * 16);
+    r.pm[i] = (float)((int)(mw & 0xffu) * s0 + (int)((mw >> 8) & 0xffu) * s1);
+  }
+  r.ddm = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
   return r;
 }
 
 // k_quants.c:3174-3262
-__device__ __forceinline__ BlockTerms block_terms(const RawQ5K& raw, int b, const ActView& a, int t) {
-  const int4 c0 = raw.c0, c1 = raw.c1, ch = raw.ch;
-  const uint32_t hb[2] = {raw.hb0, raw.hb1};
-  const ActBlock ab = load_act_block(a, b, t);
+__device__ __forceinline__ BlockTerms block_terms(const RawQ5K& raw, int b, const ActView& a, int u) {
+  const int4 ch = raw.ch;
   uint32_t sc03, sc47, m03, m47;
   unpack_k4((uint32_t)ch.y, (uint32_t)ch.z, (uint32_t)ch.w, sc03, sc47, m03, m47);
-  float pv[2];
+  BlockTerms r;
+  const float yd = a.d[b];
 #pragma unroll
-  for (int e = 0; e < 2; e++) {
-    const int4 q = e ? c1 : c0;
+  for (int e = 0; e < KQ_NA; e++) {
+    const int4 q = raw.c[e];
+    const uint32_t hb = raw.hb[e];
     const uint32_t qv[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
+    int av[8];
+    load_act_lane(a, b, u + KQ_LPR * e, av);
     int dp[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {   // bit s of a qh byte: 5th bit of the element in sub-block s
-      const uint32_t lo = (qv[j] & 0x0f0f0f0fu) | (((hb[e] >> (2 * j)) & 0x01010101u) << 4);
-      const uint32_t hi = ((qv[j] >> 4) & 0x0f0f0f0fu) | (((hb[e] >> (2 * j + 1)) & 0x01010101u) << 4);
+      const uint32_t lo = (qv[j] & 0x0f0f0f0fu) | (((hb >> (2 * j)) & 0x01010101u) << 4);
+      const uint32_t hi = ((qv[j] >> 4) & 0x0f0f0f0fu) | (((hb >> (2 * j + 1)) & 0x01010101u) << 4);
       dp[2 * j] = __dp4a((int)lo, av[2 * j], 0);
       dp[2 * j + 1] = __dp4a((int)hi, av[2 * j + 1], 0);
     }
-    pv[e] = (float)scale_fold(dp, sc03, sc47);
+    r.p[e] = (float)scale_fold(dp, sc03, sc47);
   }
-  BlockTerms r;
-  r.p0 = pv[0]; r.p1 = pv[1];
-  r.dd = __fmul_rn(ab.yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
-  int hsum = 0;   // scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]) — used by lane t == 0 only
-  if (t == 0) {
+  r.dd = __fmul_rn(yd, h2f((uint16_t)((uint32_t)ch.x & 0xffffu)));
+  int hsum = 0;   // scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]) — used by lane u == 0 only
+  if (u == 0) {
 #pragma unroll
     for (int k = 0; k < 8; k++) hsum += CTB_BYTE(k < 4 ? m03 : m47, k & 3) * ((int)a.bs[b * 16 + 2 * k] + (int)a.bs[b * 16 + 2 * k + 1]);
   }
-  r.pm = (float)hsum;
-  r.ddm = __fmul_rn(-ab.yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
+#pragma unroll
+  for (int i = 0; i < KQ_NM; i++) r.pm[i] = i == 0 ? (float)hsum : 0.f;
+  r.ddm = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)ch.x >> 16)));
   return r;
 }
 
 // k_quants.c:3794-3872
-__device__ __forceinline__ BlockTerms block_terms(const RawQ6K& raw, int b, const ActView& a, int t) {
-  const int4 ql0 = raw.ql0, ql1 = raw.ql1, scv = raw.scv;
-  const int2 qh0 = raw.qh0, qh1 = raw.qh1;
+__device__ __forceinline__ BlockTerms block_terms(const RawQ6K& raw, int b, const ActView& a, int u) {
+  const int4 scv = raw.scv;
   const float dw = h2f(raw.d);
-  const ActBlock ab = load_act_block(a, b, t);
   const uint32_t scw[4] = {(uint32_t)scv.x, (uint32_t)scv.y, (uint32_t)scv.z, (uint32_t)scv.w};
-  float pv[2];
+  BlockTerms r;
 #pragma unroll
-  for (int e = 0; e < 2; e++) {   // e = 0: AVX lane t (elements 0..15 of each 32-group, even scales); e = 1: lane t+4 (odd scales)
-    const int4 ql = e ? ql1 : ql0;   // words: (jj=0,v=0) (0,1) (1,0) (1,1)
-    const int2 qh = e ? qh1 : qh0;   // words: jj=0, jj=1
+  for (int e = 0; e < KQ_NA; e++) {   // AVX lane l: l < 4 = elements 0..15 of each 32-group (even scales), l >= 4 = elements 16..31 (odd scales)
+    const int l = u + KQ_LPR * e, par = l >> 2;
+    const int4 ql = raw.ql[e];       // words: (jj=0,v=0) (0,1) (1,0) (1,1)
+    const int2 qh = raw.qh[e];       // words: jj=0, jj=1
     const uint32_t A[2] = {(uint32_t)ql.x, (uint32_t)ql.z}, B[2] = {(uint32_t)ql.y, (uint32_t)ql.w}, H[2] = {(uint32_t)qh.x, (uint32_t)qh.y};
-    const int av[8] = {ab.a[e][0].x, ab.a[e][0].y, ab.a[e][0].z, ab.a[e][0].w, ab.a[e][1].x, ab.a[e][1].y, ab.a[e][1].z, ab.a[e][1].w};
+    int av[8];
+    load_act_lane(a, b, l, av);
     int sumi = 0;
 #pragma unroll
     for (int jj = 0; jj < 2; jj++) {
@@ -479,37 +492,59 @@ __device__ __forceinline__ BlockTerms block_terms(const RawQ6K& raw, int b, cons
 #pragma unroll
       for (int m = 0; m < 4; m++) {
         const int aw = av[jj * 4 + m];
-        const int sidx = 8 * jj + 2 * m + e;   // int8 scale of this 16-element sub-block
+        const int sidx = 8 * jj + 2 * m + par;   // int8 scale of this 16-element sub-block
         const int scale = (int)(int8_t)CTB_BYTE(scw[sidx >> 2], sidx & 3);
         // (q6 - 32)·q8 = u·q8 - 32·Σq8, as the AVX2 kernel does with maddubs(m32s, q8)
         sumi += scale * (__dp4a((int)uu[m], aw, 0) - 32 * __dp4a(0x01010101, aw, 0));
       }
     }
-    pv[e] = (float)sumi;
+    r.p[e] = (float)sumi;
   }
-  BlockTerms r;
-  r.p0 = pv[0]; r.p1 = pv[1]; r.dd = __fmul_rn(ab.yd, dw); r.pm = 0.f; r.ddm = 0.f;
+  r.dd = __fmul_rn(a.d[b], dw); r.ddm = 0.f;
+#pragma unroll
+  for (int i = 0; i < KQ_NM; i++) r.pm[i] = 0.f;
   return r;
 }
 
 // running state of one row's fold in this lane
-struct Fold { float a0, a1, am; };
-__device__ __forceinline__ void fold_block(Fold& f, const BlockTerms& x) {
-  f.a0 = __fmaf_rn(x.dd, x.p0, f.a0);
-  f.a1 = __fmaf_rn(x.dd, x.p1, f.a1);
-  f.am = __fmaf_rn(x.ddm, x.pm, f.am);
+struct Fold { float a[KQ_NA]; float am[KQ_NM]; };
+constexpr int KQ_FOLD_FLOATS = KQ_NA + KQ_NM;
+__device__ __forceinline__ void fold_zero(Fold& f) {
+#pragma unroll
+  for (int e = 0; e < KQ_NA; e++) f.a[e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < KQ_NM; i++) f.am[i] = 0.f;
 }
-// hsum_float_8 (ggml.c:609-615) + the mins tail; finished row value in every lane of the row's 4-lane group
+__device__ __forceinline__ void fold_block(Fold& f, const BlockTerms& x) {
+#pragma unroll
+  for (int e = 0; e < KQ_NA; e++) f.a[e] = __fmaf_rn(x.dd, x.p[e], f.a[e]);
+#pragma unroll
+  for (int i = 0; i < KQ_NM; i++) f.am[i] = __fmaf_rn(x.ddm, x.pm[i], f.am[i]);
+}
+// hsum_float_8 (ggml.c:609-615): res[l] = x[l+4] + x[l]; res[0]+res[2], res[1]+res[3]; then their sum — plus the mins tail.
+// The finished row value ends up in every lane of the row's group.
 __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
-  float r = __fadd_rn(f.a1, f.a0);                        // res[l] = x[l+4] + x[l]
-  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // res[0]+res[2], res[1]+res[3]
-  r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-  float m = f.am;
-  if (type == GT_Q4_K) {                                  // acc_m: (m0+m2) + (m1+m3)
-    m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  float r, m;
+  if (KQ_LPR == 4) {
+    r = __fadd_rn(f.a[1], f.a[0]);                          // lane t holds AVX lanes t and t+4
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  } else {
+    // lane u holds AVX lanes u, u+2, u+4, u+6: (x[u+4]+x[u]) + (x[u+6]+x[u+2]) is res[0]+res[2] (u = 0) or res[1]+res[3] (u = 1)
+    r = __fadd_rn(__fadd_rn(f.a[KQ_NA / 2], f.a[0]), __fadd_rn(f.a[KQ_NA / 2 + 1 < KQ_NA ? KQ_NA / 2 + 1 : 0], f.a[1 < KQ_NA ? 1 : 0]));
+    r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+  }
+  if (type == GT_Q4_K) {                                    // acc_m: (m0+m2) + (m1+m3)
+    if (KQ_LPR == 4) {
+      m = f.am[0];
+      m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    } else {
+      m = __fadd_rn(f.am[0], f.am[KQ_NM - 1]);
+      m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    }
   } else if (type == GT_Q5_K) {
-    m = __shfl_sync(0xffffffffu, m, 0, 4);                // the scalar mins chain lives in lane t == 0
+    m = __shfl_sync(0xffffffffu, f.am[0], 0, KQ_LPR);       // the scalar mins chain lives in lane u == 0
   } else {
     return r;
   }
@@ -518,16 +553,21 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 
 // Hand-off of a row tile's fold state between consecutive warps of a CTA (see k_matvec): warp w receives at most one state
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
-constexpr int MV_SMEM_LIMIT = 227 * 1024 - ((MV_WARPS + 1) * 388 + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
-constexpr int MV_DEF_MAX = 12;   // most blocks of a mid-row segment whose terms are parked before the state arrives
+constexpr int MV_SMEM_LIMIT = 227 * 1024 - ((MV_WARPS + 1) * (KQ_FOLD_FLOATS * 128 + 4) + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
+#ifndef CTB_DEF_MAX
+#define CTB_DEF_MAX 12
+#endif
+constexpr int MV_DEF_MAX = CTB_DEF_MAX;   // most blocks of a mid-row segment whose terms are parked before the state arrives
 #ifndef CTB_RING
 #define CTB_RING 2
 #endif
 constexpr int MV_RING = CTB_RING;     // blocks per lane in flight in the register pipeline (measured: 2 > 3 > 1 > 4 once L2 is prefetched)   // most blocks of a mid-row segment whose terms are parked before the state arrives
+constexpr int KQ_PARK_F4 = (KQ_NA + KQ_NM + 1 + 3) / 4;   // float4s per lane and parked block: p[], pm[], and dd or ddm
+constexpr int KQ_PARK_BYTES = KQ_PARK_F4 * 16 * 32;       // per warp and parked block
 struct Chain {
-  float4* buf;                   // warp-private [def_max][32] parked block terms
+  float4* buf;                   // warp-private [def_max][KQ_PARK_F4][32] parked block terms
   int def_max;
-  volatile float* mail_out;      // [3][32] floats, the NEXT warp's mailbox
+  volatile float* mail_out;      // [KQ_FOLD_FLOATS][32] floats, the NEXT warp's mailbox
   volatile int* flag_out;
   volatile float* mail_in;       // this warp's mailbox
   volatile int* flag_in;
@@ -536,12 +576,12 @@ struct Chain {
 // Ask the memory system for blocks [b0, b1) of this lane's row right away (L2 prefetch, no registers held): the 4 lanes of a
 // row take turns over its 128-byte lines.  The register pipeline below then finds its data in L2.
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0, int b1, int t) {
-  for (int b = b0 + t; b < b1; b += 4) {
+__device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0, int b1, int u) {
+  for (int b = b0 + u; b < b1; b += KQ_LPR) {
     prefetch_l2(w.qs + (rb + b) * 128);
     if (w.type == GT_Q6_K && (b & 1) == 0) prefetch_l2(w.qh + (rb + b) * 64);
-    if (w.type == GT_Q5_K && (b & 3) == t) prefetch_l2(w.qh + (rb + b) * 32);
-    if ((b & 7) == t || b - t == b0) prefetch_l2(w.sc + (rb + b) * 16);
+    if (w.type == GT_Q5_K && (b & 3) == 0) prefetch_l2(w.qh + (rb + b) * 32);
+    if ((b & 7) < KQ_LPR || b - u == b0) prefetch_l2(w.sc + (rb + b) * 16);
   }
 }
 
@@ -549,7 +589,7 @@ __device__ __forceinline__ void prefetch_row(const DevMat& w, size_t rb, int b0,
 template <typename Raw, typename Sink>
 __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0, int b1, const ActView& a, int lane, Sink sink) {
   constexpr int D = MV_RING;
-  const int t = lane & 3;
+  const int t = lane % KQ_LPR;   // which of the row's lanes this is
   if (b0 >= b1) return;
   Raw ring[D];
   const int last = b1 - 1;
@@ -565,7 +605,7 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
     for (int i = 0; i < D; i++) {
       CTB_PIN();
 #if CTB_PF == 2
-      if (b + i + CTB_PFD < b1 && ((b + i) & 3) == t) {   // rolling L2 prefetch: the row's block CTB_PFD ahead, one lane of four per block
+      if (b + i + CTB_PFD < b1 && ((b + i) % KQ_LPR) == t) {   // rolling L2 prefetch: the row's block CTB_PFD ahead, one lane of the row per block
         prefetch_l2(w.qs + (rb + b + i + CTB_PFD) * 128);
         if (((b + i) & 7) < 4) prefetch_l2(w.sc + (rb + b + i + CTB_PFD) * 16);
       }
@@ -587,28 +627,53 @@ template <typename Raw>
 __device__ __forceinline__ bool run_segment_typed(const DevMat w, int row, int b0, int b1, const ActView& a, int lane, const Chain& ch, float& out) {
   const int nb = w.nb;
   const size_t rb = (size_t)row * nb;
-  Fold f{0.f, 0.f, 0.f};
+  Fold f;
+  fold_zero(f);
+  const int u = lane % KQ_LPR, lead = lane - u;
   int bd = b0;
   if (b0 > 0) {
     bd = min(b1, b0 + ch.def_max);
-    // parked per block and lane: {p0, p1, pm, (t == 0 ? dd : ddm)} — dd and ddm are the same for the 4 lanes of a row
+    // parked per block and lane: p[], pm[] and (u == 0 ? dd : ddm) — dd and ddm are the same for all lanes of a row
     stream_blocks<Raw>(w, rb, b0, bd, a, lane, [&](int b, const BlockTerms& x) {
-      ch.buf[(size_t)(b - b0) * 32 + lane] = make_float4(x.p0, x.p1, x.pm, (lane & 3) == 0 ? x.dd : x.ddm);
+      float v[KQ_PARK_F4 * 4];
+#pragma unroll
+      for (int e = 0; e < KQ_NA; e++) v[e] = x.p[e];
+#pragma unroll
+      for (int i = 0; i < KQ_NM; i++) v[KQ_NA + i] = x.pm[i];
+      v[KQ_NA + KQ_NM] = u == 0 ? x.dd : x.ddm;
+#pragma unroll
+      for (int q = 0; q < KQ_PARK_F4; q++)
+        ch.buf[((size_t)(b - b0) * KQ_PARK_F4 + q) * 32 + lane] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     });
     while (*ch.flag_in == 0) { }
     __syncwarp();
-    f.a0 = ch.mail_in[lane]; f.a1 = ch.mail_in[32 + lane]; f.am = ch.mail_in[64 + lane];
+#pragma unroll
+    for (int e = 0; e < KQ_NA; e++) f.a[e] = ch.mail_in[e * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < KQ_NM; i++) f.am[i] = ch.mail_in[(KQ_NA + i) * 32 + lane];
     for (int b = b0; b < bd; b++) {
-      const float4 v = ch.buf[(size_t)(b - b0) * 32 + lane];
-      BlockTerms x; x.p0 = v.x; x.p1 = v.y; x.pm = v.z;
-      x.dd = __shfl_sync(0xffffffffu, v.w, lane & ~3);
-      x.ddm = __shfl_sync(0xffffffffu, v.w, (lane & ~3) + 1);
+      float v[KQ_PARK_F4 * 4];
+#pragma unroll
+      for (int q = 0; q < KQ_PARK_F4; q++) {
+        const float4 t4 = ch.buf[((size_t)(b - b0) * KQ_PARK_F4 + q) * 32 + lane];
+        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+      }
+      BlockTerms x;
+#pragma unroll
+      for (int e = 0; e < KQ_NA; e++) x.p[e] = v[e];
+#pragma unroll
+      for (int i = 0; i < KQ_NM; i++) x.pm[i] = v[KQ_NA + i];
+      x.dd = __shfl_sync(0xffffffffu, v[KQ_NA + KQ_NM], lead);
+      x.ddm = __shfl_sync(0xffffffffu, v[KQ_NA + KQ_NM], lead + 1);
       fold_block(f, x);
     }
   }
   stream_blocks<Raw>(w, rb, bd, b1, a, lane, [&](int, const BlockTerms& x) { fold_block(f, x); });
   if (b1 < nb) {
-    ch.mail_out[lane] = f.a0; ch.mail_out[32 + lane] = f.a1; ch.mail_out[64 + lane] = f.am;
+#pragma unroll
+    for (int e = 0; e < KQ_NA; e++) ch.mail_out[e * 32 + lane] = f.a[e];
+#pragma unroll
+    for (int i = 0; i < KQ_NM; i++) ch.mail_out[(KQ_NA + i) * 32 + lane] = f.am[i];
     __threadfence_block();
     __syncwarp();
     if (lane == 0) *ch.flag_out = 1;
@@ -710,7 +775,7 @@ __device__ __forceinline__ void store_epilogue(const MVSeg& sg, const MVParams& 
   sg.out[row] = v;
 }
 
-constexpr int MV_KQ_ROWS = 8;      // K-quants: rows per tile (4 lanes per row)
+constexpr int MV_KQ_ROWS = 32 / KQ_LPR;   // K-quants: rows per tile (one warp)
 
 // rows one work unit (one warp task) covers for a weight type
 __host__ __device__ inline int rows_per_unit(int type) {
@@ -767,7 +832,7 @@ template <int KT>
 static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
-  __shared__ float mailbox[MV_WARPS + 1][96];
+  __shared__ float mailbox[MV_WARPS + 1][KQ_FOLD_FLOATS * 32];
   __shared__ int flags[MV_WARPS + 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool kq = KT != 0 || type_is_kquant(p.seg[0].w.type);
@@ -789,11 +854,11 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
       const int b0 = pos % nb, len = min(nb - b0, e0 - pos);
       const int s = ts.locate(tile);
       const DevMat& w = p.seg[s].w;
-      const int row = min(tile * MV_KQ_ROWS + (lane >> 2), w.M - 1);
+      const int row = min(tile * MV_KQ_ROWS + lane / KQ_LPR, w.M - 1);
 #if CTB_PF == 1
-      prefetch_row(w, (size_t)row * nb, b0, b0 + len, lane & 3);
+      prefetch_row(w, (size_t)row * nb, b0, b0 + len, lane % KQ_LPR);
 #elif CTB_PF == 2
-      prefetch_row(w, (size_t)row * nb, b0, min(b0 + len, b0 + CTB_PFD), lane & 3);
+      prefetch_row(w, (size_t)row * nb, b0, min(b0 + len, b0 + CTB_PFD), lane % KQ_LPR);
 #endif
       pos += len;
     }
@@ -810,7 +875,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
     Chain ch;
     uint8_t* const dyn = smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15);
     ch.def_max = p.def_max;
-    ch.buf = (float4*)dyn + (size_t)warp * p.def_max * 32;
+    ch.buf = (float4*)dyn + (size_t)warp * p.def_max * KQ_PARK_F4 * 32;
     ch.mail_in = mailbox[warp]; ch.flag_in = &flags[warp];
     ch.mail_out = mailbox[warp + 1]; ch.flag_out = &flags[warp + 1];
     const int a0 = s0 % nb;
@@ -824,10 +889,10 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
       else { tile = T0 + s0 / nb; b0 = a0; b1 = a0 + def_len; }
       const int s = ts.locate(tile);
       const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
-      const int row = tile * MV_KQ_ROWS + (lane >> 2);
+      const int row = tile * MV_KQ_ROWS + lane / KQ_LPR;
       float v = 0.f;
       const bool done = run_segment<KT>(sg.w, min(row, sg.w.M - 1), b0, b1, a, lane, ch, v);
-      if (done && (lane & 3) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
+      if (done && (lane % KQ_LPR) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
     }
     return;
   }
@@ -874,8 +939,8 @@ inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
     const long nb = p.K / 256, tiles_per_cta = (units + L.grid - 1) / L.grid;
     const long range = (tiles_per_cta * nb + MV_WARPS - 1) / MV_WARPS;
     const long need = std::min<long>(range, nb - 1);
-    p.def_max = (int)std::max<long>(1, std::min<long>(std::min<long>(MV_DEF_MAX, need), room / (MV_WARPS * 512)));
-    L.smem = act + (size_t)MV_WARPS * p.def_max * 512;
+    p.def_max = (int)std::max<long>(1, std::min<long>(std::min<long>(MV_DEF_MAX, need), room / (MV_WARPS * KQ_PARK_BYTES)));
+    L.smem = act + (size_t)MV_WARPS * p.def_max * KQ_PARK_BYTES;
   } else {
     L.grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)n_sm));
     L.smem = act;

@@ -60,6 +60,9 @@ void ctransformers_llm_reset(LLM* llm);                     /* llm.cc:134 */
 int ctb_abi_version(void);
 double ctb_llm_last_eval_ms(LLM* llm);              /* CUDA-event time of the last batch_eval / decode_greedy */
 long ctb_llm_launches_per_token(LLM* llm);          /* kernels in one decode step's CUDA graph */
+/* batch_eval calls answered by the step the engine had already started for the greedy next token (engine.cu: after_eval);
+ * CTB_NO_SPEC=1 in the environment turns that look-ahead off. */
+long ctb_llm_speculative_hits(LLM* llm);
 unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm); /* algorithmic weight bytes one decode step reads */
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream);        /* run on a caller-owned cudaStream_t */
 /* n_steps greedy decode steps with the token fed back on the device (no host round trip per token);

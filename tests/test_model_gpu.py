@@ -155,3 +155,25 @@ def test_create_failure_modes(tmp_path):
         AutoModelForCausalLM.from_pretrained(str(bad))
     with pytest.raises(ValueError):
         AutoModelForCausalLM.from_pretrained(str(tmp_path / "nope.gguf"))
+
+
+def test_greedy_lookahead_hits_and_misses_match_the_oracle(model_dir, lib):
+    """The engine starts the step for the greedy next token while the host samples (engine.cu: after_eval).  A run of greedy
+    tokens (look-ahead hits), then off-greedy tokens (misses that must overwrite the guessed step), then greedy again:
+    every logits vector must be the oracle's for the same token sequence."""
+    name = "llama_tiny_q4km"
+    path, ctx = modelcases.build(name, model_dir)
+    llm = load(path, ctx)
+    orc = refs.OracleModel(path, ctx)
+    seq = modelcases.prompt_for(name)[:9]
+    llm.eval(seq, batch_size=8)
+    want = orc.eval(seq, batch_size=8).copy()
+    hits0 = llm.ctb_llm_speculative_hits()
+    for step in range(16):
+        got = np.array(llm.logits, dtype=np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"step {step}"
+        greedy = int(np.argmax(got))
+        tok = greedy if step not in (6, 7, 12) else (greedy + 17) % llm.vocab_size
+        llm.eval([tok])
+        want = orc.eval([tok]).copy()
+    assert llm.ctb_llm_speculative_hits() - hits0 >= 4
