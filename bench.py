@@ -38,8 +38,20 @@ MODEL_DIR = Path(os.environ.get("CTB_MODEL_DIR", "/tmp/ctb_models"))
 REF_SO = ROOT / "oracle" / "_ref" / "libctransformers_ref.so"
 
 
+# --workload: the default is the BASELINE.json headline (configs[1]); "falcon7b" is configs[3] (not a driver bench line)
+WORKLOADS = {
+    "llama2-7b": dict(file="llama2-7b-shaped.Q4_K_M.synthetic.gguf", arch="llama", shape="LLAMA2_7B", ftype="Q4_K_M", lo=259,
+                      metric="decode tokens/s Llama-2-7B Q4_K_M b=1", dtype="int8 (q4_K/q6_K weights x q8_K activations, dp4a), fp32 combine",
+                      name="Llama-2-7B-shaped Q4_K_M GGUF"),
+    "falcon7b": dict(file="falcon-7b-shaped.Q5_K_M.synthetic.gguf", arch="falcon", shape="FALCON_7B_SHAPED", ftype="Q5_K_M", lo=0,
+                     metric="decode tokens/s Falcon-7B Q5_K_M b=1", dtype="int8 (q5_K/q6_K/q8_0 weights x q8_K/q8_0 activations, dp4a), fp32 combine",
+                     name="Falcon-7B-shaped (n_embd 4608, multi-query) Q5_K_M GGUF"),
+}
+WL = WORKLOADS["llama2-7b"]
+
+
 def model_path():
-    return MODEL_DIR / "llama2-7b-shaped.Q4_K_M.synthetic.gguf"
+    return MODEL_DIR / WL["file"]
 
 
 def ensure_model(rank, world, barrier):
@@ -48,7 +60,7 @@ def ensure_model(rank, world, barrier):
     if rank == 0 and not p.exists():
         MODEL_DIR.mkdir(parents=True, exist_ok=True)
         tmp = p.with_suffix(".tmp")
-        synth.write_llama(tmp, synth.LLAMA2_7B, "Q4_K_M", seed=0)
+        (synth.write_llama if WL["arch"] == "llama" else synth.write_falcon)(tmp, getattr(synth, WL["shape"]), WL["ftype"], seed=0)
         tmp.rename(p)
     barrier()
     return p
@@ -56,8 +68,10 @@ def ensure_model(rank, world, barrier):
 
 def prompt_ids():
     import numpy as np
-    ids = np.random.default_rng(1).integers(259, 32000, PROMPT).tolist()
-    ids[0] = 1
+    from ctransformers_b200 import synth
+    ids = np.random.default_rng(1).integers(WL["lo"], getattr(synth, WL["shape"]).n_vocab, PROMPT).tolist()
+    if WL["arch"] == "llama":
+        ids[0] = 1
     return ids
 
 
@@ -152,14 +166,14 @@ def run_reference(args, rank, world, barrier):
     }))
 
 
-METRIC = "decode tokens/s Llama-2-7B Q4_K_M b=1"
-DTYPE = "int8 (q4_K/q6_K weights x q8_K activations, dp4a), fp32 combine"
+METRIC = WL["metric"]
+DTYPE = WL["dtype"]
 
 
 def workload_config(n):
-    return {"workload": "Llama-2-7B-shaped Q4_K_M GGUF (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode",
+    return {"workload": WL["name"] + " (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode",
             "global_batch": n, "ctx": CTX, "prompt": PROMPT, "parallelism": f"replicas x{n} (one sequence per GPU, no collective)",
-            "l2": "inputs (3.8 GB weights/step) exceed the 126 MB L2; no flush needed"}
+            "l2": "inputs (GBs of weights per step) exceed the 126 MB L2; no flush needed"}
 
 
 def main():
@@ -169,7 +183,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="llama2-7b", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global WL, METRIC, DTYPE
+    WL = WORKLOADS[args.workload]
+    METRIC, DTYPE = WL["metric"], WL["dtype"]
 
     from ctransformers_b200 import replicas
     who = replicas.Rank.from_env()
@@ -194,7 +212,7 @@ def main():
     from ctransformers_b200 import AutoModelForCausalLM, synth
     path = ensure_model(rank, world, barrier)
     llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=CTX)
-    shape = synth.LLAMA2_7B
+    shape = getattr(synth, WL["shape"])
     ids = prompt_ids()
     steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 1))
     W = max(args.warmup, 3)
@@ -256,7 +274,7 @@ def main():
     mv_achieved = wbytes / (mv_ms / 1e3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "k_matvec_traffic.json"
-    if tf.exists():
+    if tf.exists() and args.workload == "llama2-7b":
         traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch_avg")
     roofline = {
         "bound": "hbm", "kernel": "k_matvec", "achieved": mv_achieved, "peak": peak, "unit": "GB/s", "frac": mv_achieved / peak, "traffic": traffic,
