@@ -285,6 +285,11 @@ void Engine::launch_attn(const AttnParams& ap) {
 
 void Engine::launch_matvec(MVParams& p, int kind) {
   if (matvec_only_ && !((matvec_mask_ >> kind) & 1)) return;
+  if (trace_buf_) {
+    p.trace = trace_buf_ + (size_t)trace_launch_ * sm_count_ * (4 + MV_WARPS);
+    trace_kind_.push_back(kind);
+    trace_launch_++;
+  }
   p.silu_tab = silu_tab_;
   p.gelu_tab = gelu_tab_;
   const MVLaunch L = matvec_launch_shape(p, sm_count_);
@@ -447,6 +452,54 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
   }
   for (cudaEvent_t e : prof_ev_) cudaEventDestroy(e);
   prof_ev_.clear(); prof_kind_.clear();
+  return n;
+}
+
+// One decode step replayed as a CUDA graph in which every k_matvec CTA stamps %globaltimer at entry, when its dependency is
+// released, when its input is staged and when each warp finishes: the in-graph anatomy of the per-launch fixed cost.
+// out: per launch {kind, grid, then per CTA (4 + MV_WARPS) stamps}; returns the number of launches, or -needed-size.
+long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
+  CTB_CUDA(cudaSetDevice(device_));
+  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  const size_t per_launch = (size_t)sm_count_ * (4 + MV_WARPS);
+  const size_t max_launches = (size_t)hp_.n_layer * 5 + 2;
+  unsigned long long* buf = nullptr;
+  CTB_CUDA(cudaMalloc(&buf, max_launches * per_launch * 8));
+  CTB_CUDA(cudaMemset(buf, 0, max_launches * per_launch * 8));
+  cudaStream_t user = stream_, cap;
+  CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  const long keep = launches_per_step_;
+  cudaGraphExec_t ex = nullptr;
+  stream_ = cap; trace_buf_ = buf; trace_launch_ = 0; trace_kind_.clear();
+  try {
+    cudaGraph_t g;
+    CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+    enqueue_step(true, false);
+    CTB_CUDA(cudaStreamEndCapture(cap, &g));
+    CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
+    cudaGraphDestroy(g);
+  } catch (...) { stream_ = user; trace_buf_ = nullptr; launches_per_step_ = keep; cudaStreamDestroy(cap); cudaFree(buf); throw; }
+  stream_ = user; trace_buf_ = nullptr; launches_per_step_ = keep;
+  cudaStreamDestroy(cap);
+  const long n = trace_launch_;
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
+  for (int rep = 0; rep < 3; rep++) {      // the last replay is the one read back (warm)
+    h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
+    CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
+    CTB_CUDA(cudaGraphLaunch(ex, stream_));
+    CTB_CUDA(cudaStreamSynchronize(stream_));
+  }
+  cudaGraphExecDestroy(ex);
+  const long need = n * (long)(2 + per_launch);
+  if (need > cap_words) { cudaFree(buf); return -need; }
+  std::vector<unsigned long long> h(n * per_launch);
+  CTB_CUDA(cudaMemcpy(h.data(), buf, h.size() * 8, cudaMemcpyDeviceToHost));
+  cudaFree(buf);
+  for (long i = 0; i < n; i++) {
+    unsigned long long* o = out + i * (2 + per_launch);
+    o[0] = (unsigned long long)trace_kind_[i]; o[1] = (unsigned long long)sm_count_;
+    memcpy(o + 2, h.data() + i * per_launch, per_launch * 8);
+  }
   return n;
 }
 

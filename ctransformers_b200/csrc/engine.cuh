@@ -50,6 +50,7 @@ class Engine {
   // One eager (un-graphed) decode step at n_past with a CUDA event after every kernel; accumulates the
   // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
   double time_matvec_only(int reps, long* launches, unsigned mask = 0);
+  long trace_step(int token, int n_past, unsigned long long* out, long cap_words);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
 
   float* logits() { return h_logits_; }
@@ -108,6 +109,9 @@ class Engine {
   void launch_matvec(struct MVParams& p, int kind);
   void launch_attn(const struct AttnParams& ap);
   bool profiling_ = false;
+  unsigned long long* trace_buf_ = nullptr;   // trace_step: device stamps, one slice per k_matvec launch
+  long trace_launch_ = 0;
+  std::vector<int> trace_kind_;
   bool matvec_only_ = false;
   unsigned matvec_mask_ = ~0u;  // time_matvec_only: bit k set = launches of kind k are kept
   long matvec_launches_ = 0;   // k_matvec launches of the step being enqueued

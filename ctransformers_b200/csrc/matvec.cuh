@@ -66,6 +66,7 @@ struct MVParams {
   MVSeg seg[MV_MAX_SEG];
   const uint16_t* silu_tab;   // 65536-entry fp16 tables built on the host exactly like ggml.c:4319-4333
   const uint16_t* gelu_tab;
+  unsigned long long* trace;   // optional, per CTA 4 + MV_WARPS globaltimer stamps: entry, dependency released, input staged, (unused), each warp's end
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -838,6 +839,8 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
   const bool kq = KT != 0 || type_is_kquant(p.seg[0].w.type);
   if (threadIdx.x <= MV_WARPS) flags[threadIdx.x] = 0;
   pdl_trigger();
+  unsigned long long* const tr = p.trace ? p.trace + (size_t)blockIdx.x * (4 + MV_WARPS) : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
 
   // ---- this warp's share of the weights, known before any input is: ask L2 for it while the prologue runs
   TileSpace ts;
@@ -867,11 +870,13 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
   NormPre np;
   preload_norm(np, p.norm_w, p.norm_b, p.norm_mode, p.K);
   pdl_wait();   // everything above touched only weights and shared memory; the input vector is the predecessor's output
+  if (tr && threadIdx.x == 0) tr[1] = globaltimer_ns();
   stage_activation(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
   const ActView a = act_view(p.act, p.K, smem);
+  if (tr && threadIdx.x == 0) tr[2] = globaltimer_ns();
 
   if (kq) {
-    if (s0 >= e0) return;
+    if (s0 >= e0) { if (tr && lane == 0) tr[4 + warp] = globaltimer_ns(); return; }
     Chain ch;
     uint8_t* const dyn = smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15);
     ch.def_max = p.def_max;
@@ -894,6 +899,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
       const bool done = run_segment<KT>(sg.w, min(row, sg.w.M - 1), b0, b1, a, lane, ch, v);
       if (done && (lane % KQ_LPR) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
     }
+    if (tr && lane == 0) tr[4 + warp] = globaltimer_ns();
     return;
   }
   if (KT != 0) return;   // specialised instances carry no code for the other weight types

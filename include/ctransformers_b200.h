@@ -75,6 +75,9 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
 /* The mat-vec launches of one decode step alone (same kernels, parameters and order; attention, embedding and argmax left
  * out), replayed reps times as a CUDA graph between two CUDA events: returns milliseconds per step, < 0 on error;
  * *launches = mat-vec launches per step.  KV cache and logits are not meaningful afterwards. */
+/* One decode step as a CUDA graph whose k_matvec CTAs stamp %globaltimer (ns): per launch out holds {kind, n_cta} and, per CTA,
+ * {entry, dependency released, input staged, 0, end of warp 0..15}.  Returns the launches written, or -(words needed). */
+long ctb_llm_trace_step(LLM* llm, int token, int n_past, unsigned long long* out, long cap_words);
 double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches);
 /* Same, restricted to the launches whose kind bit is set in kind_mask (bit 0 QKV, 1 attention output, 2 FFN gate+up,
  * 3 FFN down, 4 output head; 0 = all): per-projection timing under in-graph launch conditions. */
