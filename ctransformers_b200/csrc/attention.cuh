@@ -180,13 +180,20 @@ __device__ __forceinline__ float attn_reduce_f32x8(float v) {
 // gives n_head * hd/32 CTAs per token instead of n_head.  The CTA with blockIdx.z == 0 of the first head of each KV group
 // writes that group's K row; V channels are written by the CTAs (first head of the group) that own them.  The current
 // position is always taken from the freshly computed k/v, never read back from the cache, so there is no ordering hazard.
-static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// DEP = 0: a kernel of its own, q/k/v come from the previous kernel (griddepcontrol.wait).
+// DEP = 1: the tail of the QKV mat-vec launch (matvec.cuh): q/k/v rows come from other CTAs of the SAME launch, which count
+//          their finished row tiles in *dep_counter; the body waits until all dep_target tiles are in.
+template <int DEP>
+__device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, const int h, const int n, const int cg, const int* dep_counter, const int dep_target) {
   __shared__ float red_f[ATTN_WARPS];
   __shared__ double red_d[ATTN_WARPS];
-  const int h = blockIdx.x, n = blockIdx.y, cg = blockIdx.z;
   const int hd = p.hd, per = hd >> 5;
-  pdl_trigger();
   // Everything up to pdl_wait() reads only what earlier steps left behind (device state, RoPE table, cached K/V rows of
   // older positions): it overlaps the tail of the QKV kernel.  q/k/v of this token are read after the wait.
   const int pos = p.state[1] + n;
@@ -224,7 +231,12 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
     }
   }
   if (threadIdx.x < hd / 2) cs_pre = p.rope[(size_t)pos * (hd / 2) + threadIdx.x];
-  pdl_wait();
+  if (DEP == 0) {
+    pdl_wait();
+  } else {
+    if (threadIdx.x == 0) while (ld_acquire_gpu(dep_counter) < dep_target) { }
+    __syncthreads();
+  }
 
   {  // RoPE (pairs) + f16 conversion of q, k, v for this position
     const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
@@ -235,15 +247,15 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
       const float2 cs = i == (int)threadIdx.x ? cs_pre : p.rope[(size_t)pos * (hd / 2) + i];
       const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
       float o0, o1;
-      rope_pair(qv[i0], qv[i1], cs, p.neox, o0, o1);
+      rope_pair(__ldcg(qv + i0), __ldcg(qv + i1), cs, p.neox, o0, o1);
       q16[k_perm(i0, hd)] = f2h(o0); q16[k_perm(i1, hd)] = f2h(o1);
-      rope_pair(kv[i0], kv[i1], cs, p.neox, o0, o1);
+      rope_pair(__ldcg(kv + i0), __ldcg(kv + i1), cs, p.neox, o0, o1);
       const uint16_t h0 = f2h(o0), h1 = f2h(o1);
       k16[k_perm(i0, hd)] = h0; k16[k_perm(i1, hd)] = h1;
       if (kv_writer && cg == 0) { kd[k_perm(i0, hd)] = h0; kd[k_perm(i1, hd)] = h1; }
     }
     for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
-      const uint16_t hv = f2h(vv[c]);
+      const uint16_t hv = f2h(__ldcg(vv + c));
       v16[c] = hv;
       if (kv_writer && c / ATTN_CH == cg) p.vc[((size_t)kvh * hd + c) * cp + v_perm(pos)] = hv;
     }
@@ -353,6 +365,12 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
     }
     if (lane == 0) p.out[(size_t)n * p.n_head * hd + (size_t)h * hd + c] = (float)sumf;
   }
+}
+
+static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  pdl_trigger();
+  attn_body<0>(p, smem, blockIdx.x, blockIdx.y, blockIdx.z, nullptr, 0);
 }
 
 // ----------------------------------------------------------------------------------------- argmax

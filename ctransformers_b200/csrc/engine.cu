@@ -233,6 +233,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   ffn2_ = (float*)alloc((size_t)hp_.n_ff * 4);
   d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
   d_embd_ = (float*)alloc(hp_.n_embd * 4);
+  attn_cnt_ = (int*)alloc((size_t)hp_.n_layer * 4);
   CTB_CUDA(cudaMemset(d_state_, 0, 64));
   CTB_CUDA(cudaMallocHost(&h_logits_, (size_t)hp_.n_vocab * 4));
   CTB_CUDA(cudaMallocHost(&h_embd_, (size_t)hp_.n_embd * 4));
@@ -241,6 +242,7 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
 
   if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
   if (const char* e = getenv("CTB_NO_SPEC")) spec_on_ = !(e[0] == '1');
+  if (const char* e = getenv("CTB_FUSED_ATTN")) fuse_attn_ = e[0] == '1';
   CTB_CUDA(cudaMallocHost(&h_spec_tok_, 16));
   CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
@@ -311,6 +313,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
   launches_per_step_ = 0;
   matvec_launches_ = 0;
+  CTB_CUDA(cudaMemsetAsync(attn_cnt_, 0, (size_t)hp_.n_layer * 4, stream_));   // finished-tile counters of the fused QKV+attention launches
   mark(-1);
   if (!matvec_only_) {
     k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
@@ -323,6 +326,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
     const LayerW& L = layers_[il];
     uint16_t* kc = kc_ + (size_t)il * hp_.n_ctx * gqa;
     uint16_t* vc = vc_ + (size_t)il * gqa * kv_ctx_pad(hp_.n_ctx);
+    bool attn_fused = false;
     AttnParams ap{};
     ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.state = d_state_; ap.kq_scale = kq_scale;
     ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx; ap.rope = rope_; ap.neox = hp_.falcon ? 1 : 0;
@@ -335,18 +339,20 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         const DevMat* ws[3] = {&L.wq, &L.wk, &L.wv};
         float* outs[3] = {q, k, v};
         bool done[3] = {false, false, false};
+        ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
         for (int i = 0; i < 3; i++) {   // group tensors that share an activation format into one launch
           if (done[i]) continue;
           p.act = act_format_for(ws[i]->type); p.nseg = 0;
           for (int j = i; j < 3; j++)
             if (!done[j] && act_format_for(ws[j]->type) == p.act) { p.seg[p.nseg++] = seg(*ws[j], outs[j]); done[j] = true; }
+          // all of q, k, v in one K-quant launch: attention runs as that launch's tail (no kernel boundary in between)
+          attn_fused = fuse_attn_ && !matvec_only_ && !profiling_ && p.nseg == 3 && type_is_kquant(ws[0]->type);
+          if (attn_fused) { p.attn_on = 1; p.attn = ap; p.attn_counter = attn_cnt_ + il; }
           launch_matvec(p, MVK_QKV);
         }
       }
-      ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
-      if (!matvec_only_) launch_attn(ap);
+      if (!matvec_only_ && !attn_fused) { launch_attn(ap); launches_per_step_ += 1; }
       mark(1);
-      launches_per_step_ += 1;
       {  // wo + residual
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
@@ -379,6 +385,9 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.act = act_format_for(L.wqkv.type); p.nseg = 1;
         p.seg[0] = seg(L.wqkv, qkv_);
         if (fuse) { p.seg[1] = seg(L.w3, ffn_); p.nseg = 2; }   // GELU is applied by ffn_down's prologue
+        ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
+        attn_fused = fuse_attn_ && !matvec_only_ && !profiling_ && type_is_kquant(L.wqkv.type) && (!fuse || type_is_kquant(L.w3.type));
+        if (attn_fused) { p.attn_on = 1; p.attn = ap; p.attn_counter = attn_cnt_ + il; }
         launch_matvec(p, MVK_QKV);
       }
       if (!fuse) {
@@ -388,10 +397,8 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.seg[0] = seg(L.w3, ffn_);
         launch_matvec(p, MVK_UP);
       }
-      ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
-      if (!matvec_only_) launch_attn(ap);
+      if (!matvec_only_ && !attn_fused) { launch_attn(ap); launches_per_step_ += 1; }
       mark(1);
-      launches_per_step_ += 1;
       {  // attention output projection
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;

@@ -115,6 +115,8 @@ class Engine {
   bool matvec_only_ = false;
   unsigned matvec_mask_ = ~0u;  // time_matvec_only: bit k set = launches of kind k are kept
   long matvec_launches_ = 0;   // k_matvec launches of the step being enqueued
+  bool fuse_attn_ = false;     // attention as the tail of the QKV launch: bit-exact but measured slower (430 vs 485 tokens/s); CTB_FUSED_ATTN=1 turns it on
+  int* attn_cnt_ = nullptr;    // [n_layer] finished row tiles of each layer's QKV launch
   bool pdl_ = true;            // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<int> prof_kind_;

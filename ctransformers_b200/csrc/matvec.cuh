@@ -21,6 +21,7 @@
 // logits then differ by ~1e-3 (measured).  HBM traffic per launch = the weight planes once + O(K) activations from L2.
 #pragma once
 #include "device_types.cuh"
+#include "attention.cuh"
 
 namespace ctb {
 
@@ -66,6 +67,11 @@ struct MVParams {
   MVSeg seg[MV_MAX_SEG];
   const uint16_t* silu_tab;   // 65536-entry fp16 tables built on the host exactly like ggml.c:4319-4333
   const uint16_t* gelu_tab;
+  // fused attention tail (QKV launches of the decode step): after its share of the mat-vec a CTA runs attention task(s) for
+  // the token — see k_matvec.  attn_counter counts finished row tiles of this launch (zeroed before the step).
+  int attn_on;
+  AttnParams attn;
+  int* attn_counter;
   unsigned long long* trace;   // optional, per CTA 4 + MV_WARPS globaltimer stamps: entry, dependency released, input staged, (unused), each warp's end
 };
 
@@ -829,15 +835,17 @@ struct TileSpace {
 // number of weight bytes whatever the shape.  A row tile cut between warps is folded in order by handing its fp32 state from
 // warp to warp (run_segment_typed).  A warp first does the tiles it starts at block 0 (it can post their state early), then
 // the tile it joined in the middle.  Other weight types: warp tasks strided over all warps of the grid.
-template <int KT>
+template <int KT, bool ATTN>
 static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
   __shared__ float mailbox[MV_WARPS + 1][KQ_FOLD_FLOATS * 32];
   __shared__ int flags[MV_WARPS + 1];
+  __shared__ int cta_tiles;        // fused attention: row tiles this CTA finished
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool kq = KT != 0 || type_is_kquant(p.seg[0].w.type);
   if (threadIdx.x <= MV_WARPS) flags[threadIdx.x] = 0;
+  if (threadIdx.x == 0) cta_tiles = 0;
   pdl_trigger();
   unsigned long long* const tr = p.trace ? p.trace + (size_t)blockIdx.x * (4 + MV_WARPS) : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
@@ -876,30 +884,45 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
   if (tr && threadIdx.x == 0) tr[2] = globaltimer_ns();
 
   if (kq) {
-    if (s0 >= e0) { if (tr && lane == 0) tr[4 + warp] = globaltimer_ns(); return; }
-    Chain ch;
-    uint8_t* const dyn = smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15);
-    ch.def_max = p.def_max;
-    ch.buf = (float4*)dyn + (size_t)warp * p.def_max * KQ_PARK_F4 * 32;
-    ch.mail_in = mailbox[warp]; ch.flag_in = &flags[warp];
-    ch.mail_out = mailbox[warp + 1]; ch.flag_out = &flags[warp + 1];
-    const int a0 = s0 % nb;
-    const int def_len = a0 ? min(nb - a0, e0 - s0) : 0;     // the piece of a tile another warp started
-    const int sd = s0 + def_len;                              // tile-aligned from here on
-    const int ndirect = (e0 - sd + nb - 1) / nb;
-    const int nsegs = ndirect + (def_len ? 1 : 0);
-    for (int i = 0; i < nsegs; i++) {
-      int tile, b0, b1;
-      if (i < ndirect) { const int pos = sd + i * nb; tile = T0 + pos / nb; b0 = 0; b1 = min(nb, e0 - pos); }
-      else { tile = T0 + s0 / nb; b0 = a0; b1 = a0 + def_len; }
-      const int s = ts.locate(tile);
-      const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
-      const int row = tile * MV_KQ_ROWS + lane / KQ_LPR;
-      float v = 0.f;
-      const bool done = run_segment<KT>(sg.w, min(row, sg.w.M - 1), b0, b1, a, lane, ch, v);
-      if (done && (lane % KQ_LPR) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
+    int tiles_done = 0;
+    if (s0 < e0) {
+      Chain ch;
+      uint8_t* const dyn = smem + ((act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15);
+      ch.def_max = p.def_max;
+      ch.buf = (float4*)dyn + (size_t)warp * p.def_max * KQ_PARK_F4 * 32;
+      ch.mail_in = mailbox[warp]; ch.flag_in = &flags[warp];
+      ch.mail_out = mailbox[warp + 1]; ch.flag_out = &flags[warp + 1];
+      const int a0 = s0 % nb;
+      const int def_len = a0 ? min(nb - a0, e0 - s0) : 0;     // the piece of a tile another warp started
+      const int sd = s0 + def_len;                              // tile-aligned from here on
+      const int ndirect = (e0 - sd + nb - 1) / nb;
+      const int nsegs = ndirect + (def_len ? 1 : 0);
+      for (int i = 0; i < nsegs; i++) {
+        int tile, b0, b1;
+        if (i < ndirect) { const int pos = sd + i * nb; tile = T0 + pos / nb; b0 = 0; b1 = min(nb, e0 - pos); }
+        else { tile = T0 + s0 / nb; b0 = a0; b1 = a0 + def_len; }
+        const int s = ts.locate(tile);
+        const MVSeg sg = s == 0 ? p.seg[0] : (s == 1 ? p.seg[1] : p.seg[2]);   // by value: static param-bank reads, pointers in registers
+        const int row = tile * MV_KQ_ROWS + lane / KQ_LPR;
+        float v = 0.f;
+        const bool done = run_segment<KT>(sg.w, min(row, sg.w.M - 1), b0, b1, a, lane, ch, v);
+        if (done && (lane % KQ_LPR) == 0 && row < sg.w.M) store_epilogue(sg, p, row, v);
+        tiles_done += done ? 1 : 0;
+      }
     }
     if (tr && lane == 0) tr[4 + warp] = globaltimer_ns();
+    if (ATTN) {
+      // ---- attention for this token, as soon as every row tile of q, k and v is in (they come from all CTAs of this launch)
+      if (lane == 0 && tiles_done) atomicAdd(&cta_tiles, tiles_done);
+      __threadfence();                 // this lane's output rows are visible device-wide before the tiles are counted
+      __syncthreads();                 // ... and every warp is done with the activation / parking buffers
+      if (threadIdx.x == 0 && cta_tiles) atomicAdd(p.attn_counter, cta_tiles);   // one device-wide update per CTA
+      const int n_cg = p.attn.hd / ATTN_CH, n_tasks = p.attn.n_head * n_cg;
+      for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+        if (task != (int)blockIdx.x) __syncthreads();   // the previous task's shared-memory reads are over
+        attn_body<1>(p.attn, smem, task / n_cg, 0, task % n_cg, p.attn_counter, ts.ntiles);
+      }
+    }
     return;
   }
   if (KT != 0) return;   // specialised instances carry no code for the other weight types
@@ -927,7 +950,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
 }
 
 // host-side launch geometry shared by the engine and the op-level entry points
-struct MVLaunch { int grid; size_t smem; int kt; };
+struct MVLaunch { int grid; size_t smem; int kt; bool attn; };
 inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
   MVLaunch L;
   const size_t act = (act_smem_bytes(p.act, p.K) + 15) & ~(size_t)15;
@@ -935,10 +958,13 @@ inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
   long units = 0;
   for (int s = 0; s < p.nseg; s++) { const int r = rows_per_unit(p.seg[s].w.type); units += (p.seg[s].w.M + r - 1) / r; }
   L.kt = 0;
+  L.attn = false;
   p.def_max = 0;
   if (kq) {
     L.kt = p.seg[0].w.type;
     for (int s = 1; s < p.nseg; s++) if (p.seg[s].w.type != L.kt) L.kt = 0;
+    L.attn = p.attn_on != 0;
+    if (L.attn && L.kt != GT_Q4_K) L.kt = 0;   // the attention tail is instantiated for the Q4_K and the generic kernel only
     L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm));
     const long room = (long)MV_SMEM_LIMIT - (long)act;
     // a parked (mid-row) segment is never longer than a warp's range nor than a row; shared memory not asked for stays L1
@@ -947,6 +973,7 @@ inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
     const long need = std::min<long>(range, nb - 1);
     p.def_max = (int)std::max<long>(1, std::min<long>(std::min<long>(MV_DEF_MAX, need), room / (MV_WARPS * KQ_PARK_BYTES)));
     L.smem = act + (size_t)MV_WARPS * p.def_max * KQ_PARK_BYTES;
+    if (p.attn_on) L.smem = std::max(L.smem, attn_smem_bytes(p.attn.n_ctx, p.attn.hd));
   } else {
     L.grid = (int)std::max<long>(1, std::min<long>((units + MV_WARPS - 1) / MV_WARPS, (long)n_sm));
     L.smem = act;
@@ -963,19 +990,22 @@ static inline cudaError_t launch_matvec_kernel(const MVLaunch& L, cudaStream_t s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  if (L.attn) return L.kt == GT_Q4_K ? cudaLaunchKernelEx(&cfg, k_matvec<GT_Q4_K, true>, p) : cudaLaunchKernelEx(&cfg, k_matvec<0, true>, p);
   switch (L.kt) {
-    case GT_Q4_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q4_K>, p);
-    case GT_Q5_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q5_K>, p);
-    case GT_Q6_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q6_K>, p);
-    default: return cudaLaunchKernelEx(&cfg, k_matvec<0>, p);
+    case GT_Q4_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q4_K, false>, p);
+    case GT_Q5_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q5_K, false>, p);
+    case GT_Q6_K: return cudaLaunchKernelEx(&cfg, k_matvec<GT_Q6_K, false>, p);
+    default: return cudaLaunchKernelEx(&cfg, k_matvec<0, false>, p);
   }
 }
 static inline cudaError_t matvec_set_smem_limit(int bytes) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_matvec<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q4_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q5_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-  return cudaFuncSetAttribute(k_matvec<GT_Q6_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if ((e = cudaFuncSetAttribute(k_matvec<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q4_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q5_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<GT_Q6_K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_matvec<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_matvec<GT_Q4_K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 }  // namespace ctb
