@@ -168,7 +168,7 @@ __device__ __forceinline__ void preload_norm(NormPre& np, const float* nw, const
 }
 
 __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormPre& np, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
-                                                  int K, int act, uint8_t* smem, double* red, bool write_norm) {
+                                                  int K, int act, uint8_t* smem, double* red, bool write_norm, unsigned long long* t_stats = nullptr) {
   const int t = threadIdx.x, lane = t & 31;
   const int passes = (K + MV_THREADS * 16 - 1) / (MV_THREADS * 16);
   // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
@@ -216,6 +216,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     const float var = (float)(s2 / (double)K);
     scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(var, eps)));
   }
+  if (t_stats && t == 0) *t_stats = globaltimer_ns();
   // ---- normalise + quantize
   int8_t* qs = (int8_t*)smem;
   const size_t off = ((size_t)K + 15) & ~(size_t)15;
@@ -879,7 +880,7 @@ static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_co
   preload_norm(np, p.norm_w, p.norm_b, p.norm_mode, p.K);
   pdl_wait();   // everything above touched only weights and shared memory; the input vector is the predecessor's output
   if (tr && threadIdx.x == 0) tr[1] = globaltimer_ns();
-  stage_activation(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0);
+  stage_activation(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, p.act, smem, red, blockIdx.x == 0, tr ? tr + 3 : nullptr);
   const ActView a = act_view(p.act, p.K, smem);
   if (tr && threadIdx.x == 0) tr[2] = globaltimer_ns();
 
