@@ -229,6 +229,12 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
       const int t = min(warp * 8 + i, T - 1);
       kpre[i] = (t == pos) ? make_uint2(0, 0) : *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
     }
+  } else if (per == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int t = min(warp * 8 + i, T - 1);
+      kpre[i] = make_uint2((t == pos) ? 0u : *(const uint32_t*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 2), 0u);
+    }
   }
   if (threadIdx.x < hd / 2) cs_pre = p.rope[(size_t)pos * (hd / 2) + threadIdx.x];
   if (DEP == 0) {
@@ -282,6 +288,28 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
         s = __fmaf_rn(h2f((uint16_t)(kk[i].x >> 16)), q1, s);
         s = __fmaf_rn(h2f((uint16_t)(kk[i].y & 0xffff)), q2, s);
         s = __fmaf_rn(h2f((uint16_t)(kk[i].y >> 16)), q3, s);
+        s = attn_reduce_f32x8(s);
+        if (lane == 0 && t0 + i < T) sc[t0 + i] = __fmul_rn(s, p.kq_scale);
+      }
+    }
+  } else if (per == 2) {
+    // head_dim 64 (Falcon): the same 8-rows-in-flight scheme with 4-byte row pieces
+    const uint32_t qq = *(const uint32_t*)(q16 + lane * 2);
+    const float q0 = h2f((uint16_t)(qq & 0xffff)), q1 = h2f((uint16_t)(qq >> 16));
+    for (int t0 = warp * 8; t0 < T; t0 += ATTN_WARPS * 8) {
+      uint32_t kk[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int t = min(t0 + i, T - 1);
+        if (t == pos) kk[i] = *(const uint32_t*)(k16 + lane * 2);
+        else if (t0 == warp * 8) kk[i] = kpre[i].x;
+        else kk[i] = *(const uint32_t*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 2);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float s = 0.f;
+        s = __fmaf_rn(h2f((uint16_t)(kk[i] & 0xffff)), q0, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[i] >> 16)), q1, s);
         s = attn_reduce_f32x8(s);
         if (lane == 0 && t0 + i < T) sc[t0 + i] = __fmul_rn(s, p.kq_scale);
       }

@@ -359,11 +359,12 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.seg[0] = seg(L.wo, y, EPI_ADD, x);
         launch_matvec(p, MVK_WO);
       }
-      {  // ffn_norm + gate and up projections as two independent row sets (SiLU·mul is applied by the consumer's prologue)
+      {  // ffn_norm + gate and up projections as two independent row sets: silu(gate) is stored, the product with up is formed
+         // where ffn_down stages its input
         MVParams p{};
         p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
         p.act = act_format_for(L.w1.type); p.nseg = 2;
-        p.seg[0] = seg(L.w1, ffn_); p.seg[1] = seg(L.w3, ffn2_);
+        p.seg[0] = seg(L.w1, ffn_, EPI_SILU); p.seg[1] = seg(L.w3, ffn2_);
         launch_matvec(p, MVK_UP);
       }
       {  // w2 on silu(gate)*up, + residual
@@ -384,7 +385,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.norm_w = two_norms ? L.attn_norm2 : L.attn_norm; p.norm_b = two_norms ? L.attn_norm2_b : L.attn_norm_b;
         p.act = act_format_for(L.wqkv.type); p.nseg = 1;
         p.seg[0] = seg(L.wqkv, qkv_);
-        if (fuse) { p.seg[1] = seg(L.w3, ffn_); p.nseg = 2; }   // GELU is applied by ffn_down's prologue
+        if (fuse) { p.seg[1] = seg(L.w3, ffn_, EPI_GELU); p.nseg = 2; }
         ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
         attn_fused = fuse_attn_ && !matvec_only_ && !profiling_ && type_is_kquant(L.wqkv.type) && (!fuse || type_is_kquant(L.w3.type));
         if (attn_fused) { p.attn_on = 1; p.attn = ap; p.attn_counter = attn_cnt_ + il; }
@@ -394,7 +395,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         MVParams p{};
         p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd; p.norm_w = L.attn_norm; p.norm_b = L.attn_norm_b;
         p.act = act_format_for(L.w3.type); p.nseg = 1;
-        p.seg[0] = seg(L.w3, ffn_);
+        p.seg[0] = seg(L.w3, ffn_, EPI_GELU);
         launch_matvec(p, MVK_UP);
       }
       if (!matvec_only_ && !attn_fused) { launch_attn(ap); launches_per_step_ += 1; }
@@ -407,7 +408,7 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
       }
       {  // ffn_down, then + attn_out, then + layer input (llama.cpp:2767-2771 order)
         MVParams p{};
-        p.x = ffn_; p.x_mode = 2; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, y, EPI_ADD2, attn_o_, x);
         launch_matvec(p, MVK_DOWN);
       }

@@ -41,7 +41,7 @@ constexpr int MV_ROWS = 4;   // Q4_0 / Q8_0: rows per warp (one per 8-lane group
 constexpr int MV_MAX_SEG = 3;
 
 enum : int { NORM_NONE = 0, NORM_RMS = 1, NORM_LAYER = 2 };
-enum : int { EPI_STORE = 0, EPI_ADD = 1, EPI_GELU = 2, EPI_ADD2 = 3 };
+enum : int { EPI_STORE = 0, EPI_ADD = 1, EPI_GELU = 2, EPI_ADD2 = 3, EPI_SILU = 4 };   // GELU / SILU: the reference's fp16-table activation of the row value
 
 struct MVSeg {
   DevMat w;
@@ -55,7 +55,7 @@ struct MVParams {
   const float* x;        // [K] f32 input
   const float* x2;       // x_mode 1: second operand
   int def_max;           // set by matvec_launch_shape: blocks of parked terms per warp that fit in shared memory
-  int x_mode;            // 0: x;  1: silu_table(x) * x2 (ggml_silu + ggml_mul, llama.cpp:2438-2443);  2: gelu_table(x) (falcon)
+  int x_mode;            // 0: x;  1: x * x2 (ggml_mul of silu(gate) and up, llama.cpp:2438-2443; the SiLU table is applied by the gate rows' epilogue)
   const float* norm_w;   // [K] or null
   const float* norm_b;   // [K] or null (LayerNorm bias)
   float* norm_out;       // optional [K]: CTA 0 writes the normalised vector (result_norm / embeddings)
@@ -147,14 +147,11 @@ __device__ __forceinline__ uint32_t pack4(const int* q) {
 // gate and up can be two independent row sets there.
 __device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid, float (&v)[16]) {
   load16(xs.x + base, valid, v);
-  if (xs.x_mode == 1) {
+  if (xs.x_mode == 1) {          // x = silu_table(gate) (applied once, where the gate row was produced); input = x * up (ggml_mul)
     float u[16];
     load16(xs.x2 + base, valid, u);
 #pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = __fmul_rn(h2f(__ldg(xs.silu_tab + f2h(v[e]))), u[e]);
-  } else if (xs.x_mode == 2) {
-#pragma unroll
-    for (int e = 0; e < 16; e++) v[e] = h2f(__ldg(xs.gelu_tab + f2h(v[e])));
+    for (int e = 0; e < 16; e++) v[e] = __fmul_rn(v[e], u[e]);
   }
 }
 
@@ -618,7 +615,16 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
         if (((b + i) & 7) < 4) prefetch_l2(w.sc + (rb + b + i + CTB_PFD) * 16);
       }
 #endif
+#if defined(CTB_EXP_LOADS_ONLY)
+      if (b + i < b1) { BlockTerms z{}; const unsigned* rw = (const unsigned*)&ring[i]; unsigned acc = 0;
+#pragma unroll
+        for (unsigned k = 0; k < sizeof(Raw) / 4; k++) acc ^= rw[k];
+        z.dd = __uint_as_float(acc & 0x3fffffu); sink(b + i, z); }
+#elif defined(CTB_EXP_COMPUTE_X2)
+      if (b + i < b1) { BlockTerms z = block_terms(ring[i], b + i, a, t); CTB_PIN(); BlockTerms z2 = block_terms(ring[i], (b + i) ^ 1 < b1 ? (b + i) ^ 1 : b + i, a, t); z.dd = __fadd_rn(z.dd, __fmul_rn(z2.dd, 1e-30f)); z.p[0] = __fadd_rn(z.p[0], __fmul_rn(z2.p[0], 1e-30f)); sink(b + i, z); }
+#else
       if (b + i < b1) sink(b + i, block_terms(ring[i], b + i, a, t));
+#endif
       CTB_PIN();
       load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
     }
@@ -780,6 +786,7 @@ __device__ __forceinline__ void store_epilogue(const MVSeg& sg, const MVParams& 
   if (sg.epi == EPI_ADD) v = __fadd_rn(v, sg.res[row]);
   else if (sg.epi == EPI_ADD2) v = __fadd_rn(__fadd_rn(v, sg.res[row]), sg.res2[row]);
   else if (sg.epi == EPI_GELU) v = table_f16(p.gelu_tab, v);
+  else if (sg.epi == EPI_SILU) v = table_f16(p.silu_tab, v);
   sg.out[row] = v;
 }
 

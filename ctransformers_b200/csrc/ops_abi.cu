@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const
   for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
 }
 
-// the x_mode = 1 input path of the prologue on its own: out[i] = silu_table(gate[i]) * up[i]
+// the x_mode = 1 input path of the prologue on its own: out[i] = gate_act[i] * up[i] (gate_act = silu_table(gate), from the epilogue)
 __global__ void __launch_bounds__(MV_THREADS) k_gate_dump(const float* gate, const float* up, const uint16_t* silu_tab, int M, float* out) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
@@ -302,7 +302,7 @@ int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const f
     // as the engine does it: gate and up rows in one launch, SiLU(gate)*up where the down projection stages its input
     MVParams p{};
     p.x = dx.as<float>(); p.norm_mode = NORM_NONE; p.K = K; p.act = act_format_for(type); p.nseg = 2;
-    p.seg[0].w = w1.m; p.seg[0].out = dg.as<float>(); p.seg[1].w = w3.m; p.seg[1].out = du.as<float>();
+    p.seg[0].w = w1.m; p.seg[0].out = dg.as<float>(); p.seg[0].epi = EPI_SILU; p.seg[1].w = w3.m; p.seg[1].out = du.as<float>();
     run_matvec(p);
     const size_t smem = (size_t)M * 4 + 64;
     OPS_CUDA(cudaFuncSetAttribute(k_gate_dump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
