@@ -623,10 +623,22 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
 #elif defined(CTB_EXP_COMPUTE_X2)
       if (b + i < b1) { BlockTerms z = block_terms(ring[i], b + i, a, t); CTB_PIN(); BlockTerms z2 = block_terms(ring[i], (b + i) ^ 1 < b1 ? (b + i) ^ 1 : b + i, a, t); z.dd = __fadd_rn(z.dd, __fmul_rn(z2.dd, 1e-30f)); z.p[0] = __fadd_rn(z.p[0], __fmul_rn(z2.p[0], 1e-30f)); sink(b + i, z); }
 #else
+#if defined(CTB_LOAD_FIRST)
+      {   // refill the slot BEFORE computing on its old contents: D blocks stay in flight during the compute
+        const Raw cur = ring[i];
+        CTB_PIN();
+        load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
+        CTB_PIN();
+        if (b + i < b1) sink(b + i, block_terms(cur, b + i, a, t));
+      }
+#else
       if (b + i < b1) sink(b + i, block_terms(ring[i], b + i, a, t));
 #endif
+#endif
+#if !defined(CTB_LOAD_FIRST)
       CTB_PIN();
       load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
+#endif
     }
   }
 }

@@ -18,7 +18,8 @@ import bench  # noqa: E402
 from ctransformers_b200 import AutoModelForCausalLM  # noqa: E402
 
 path = bench.ensure_model(0, 1, lambda: None)
-llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=bench.CTX)
+import os
+llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=bench.CTX, **({'lib': os.environ['CTB_LIB']} if os.environ.get('CTB_LIB') else {}))
 ids = bench.prompt_ids()
 llm.eval(ids, batch_size=256)
 tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
