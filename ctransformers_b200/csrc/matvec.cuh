@@ -599,12 +599,7 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
   Raw ring[D];
   const int last = b1 - 1;
 #pragma unroll
-#ifdef CTB_FAKE_LOADS
-#define CTB_BLK(x) ((size_t)((x) & 7))
-#else
-#define CTB_BLK(x) (x)
-#endif
-  for (int i = 0; i < D; i++) load_raw(ring[i], w, CTB_BLK(rb + min(b0 + i, last)), t);   // tail slots re-load the last block (a cache hit)
+  for (int i = 0; i < D; i++) load_raw(ring[i], w, rb + min(b0 + i, last), t);   // tail slots re-load the last block (a cache hit)
   for (int b = b0; b < b1; b += D) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
@@ -627,7 +622,7 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
       {   // refill the slot BEFORE computing on its old contents: D blocks stay in flight during the compute
         const Raw cur = ring[i];
         CTB_PIN();
-        load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
+        load_raw(ring[i], w, rb + min(b + i + D, last), t);
         CTB_PIN();
         if (b + i < b1) sink(b + i, block_terms(cur, b + i, a, t));
       }
@@ -637,7 +632,7 @@ __device__ __forceinline__ void stream_blocks(const DevMat& w, size_t rb, int b0
 #endif
 #if !defined(CTB_LOAD_FIRST)
       CTB_PIN();
-      load_raw(ring[i], w, CTB_BLK(rb + min(b + i + D, last)), t);
+      load_raw(ring[i], w, rb + min(b + i + D, last), t);
 #endif
     }
   }

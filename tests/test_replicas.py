@@ -20,7 +20,7 @@ toks = g.gather_ints([7, 8, 9 + 0 * who.rank])
 g.barrier()
 out = {"rank": who.rank, "world": who.world, "ms": ms, "value": replicas.aggregate_tokens_per_s(who.world, 30, ms),
        "same_tokens": all(t == toks[0] for t in toks), "ref_runs": replicas.reference_rank_runs(who)}
-print("RESULT " + json.dumps(out), flush=True)
+open(os.path.join(os.environ["CTB_OUT"], f"rank{who.rank}.json"), "w").write(json.dumps(out))
 g.close()
 """
 
@@ -35,12 +35,12 @@ def test_two_rank_gloo_barrier_max_and_aggregate(tmp_path):
     import json
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, CTB_ROOT=str(ROOT))
+    env = dict(os.environ, CTB_ROOT=str(ROOT), CTB_OUT=str(tmp_path))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
-    res = sorted((json.loads(l.split("RESULT ", 1)[1]) for l in r.stdout.splitlines() if "RESULT " in l), key=lambda d: d["rank"])
+    res = [json.loads((tmp_path / f"rank{k}.json").read_text()) for k in range(2)]   # one file per rank: stdout of the ranks may interleave
     assert [d["rank"] for d in res] == [0, 1] and all(d["world"] == 2 for d in res)
     for d in res:
         assert d["ms"] == 15.0                         # max over ranks, on every rank
