@@ -35,6 +35,9 @@ namespace ctb {
 #ifndef CTB_THREADS
 #define CTB_THREADS 512
 #endif
+#ifndef CTB_CTAS_PER_SM
+#define CTB_CTAS_PER_SM 1
+#endif
 constexpr int MV_THREADS = CTB_THREADS;    // one persistent CTA per SM (<= 128 registers per thread): the activation prologue is paid once per SM
 constexpr int MV_WARPS = MV_THREADS / 32;
 constexpr int MV_ROWS = 4;   // Q4_0 / Q8_0: rows per warp (one per 8-lane group, in-lane chain)
@@ -558,7 +561,7 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 
 // Hand-off of a row tile's fold state between consecutive warps of a CTA (see k_matvec): warp w receives at most one state
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
-constexpr int MV_SMEM_LIMIT = 227 * 1024 - ((MV_WARPS + 1) * (KQ_FOLD_FLOATS * 128 + 4) + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
+constexpr int MV_SMEM_LIMIT = 227 * 1024 / CTB_CTAS_PER_SM - (CTB_CTAS_PER_SM > 1 ? 1024 : 0) - ((MV_WARPS + 1) * (KQ_FOLD_FLOATS * 128 + 4) + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
 #ifndef CTB_DEF_MAX
 #define CTB_DEF_MAX 12
 #endif
@@ -851,7 +854,7 @@ struct TileSpace {
 // warp to warp (run_segment_typed).  A warp first does the tiles it starts at block 0 (it can post their state early), then
 // the tile it joined in the middle.  Other weight types: warp tasks strided over all warps of the grid.
 template <int KT, bool ATTN>
-static __global__ void __launch_bounds__(MV_THREADS, 1) k_matvec(const __grid_constant__ MVParams p) {
+static __global__ void __launch_bounds__(MV_THREADS, CTB_CTAS_PER_SM) k_matvec(const __grid_constant__ MVParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ double red[MV_WARPS];
   __shared__ float mailbox[MV_WARPS + 1][KQ_FOLD_FLOATS * 32];
@@ -980,7 +983,7 @@ inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
     for (int s = 1; s < p.nseg; s++) if (p.seg[s].w.type != L.kt) L.kt = 0;
     L.attn = p.attn_on != 0;
     if (L.attn && L.kt != GT_Q4_K) L.kt = 0;   // the attention tail is instantiated for the Q4_K and the generic kernel only
-    L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm));
+    L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm * CTB_CTAS_PER_SM));
     const long room = (long)MV_SMEM_LIMIT - (long)act;
     // a parked (mid-row) segment is never longer than a warp's range nor than a row; shared memory not asked for stays L1
     const long nb = p.K / 256, tiles_per_cta = (units + L.grid - 1) / L.grid;
