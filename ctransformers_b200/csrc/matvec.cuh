@@ -563,7 +563,7 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
 constexpr int MV_SMEM_LIMIT = 227 * 1024 / CTB_CTAS_PER_SM - (CTB_CTAS_PER_SM > 1 ? 1024 : 0) - ((MV_WARPS + 1) * (KQ_FOLD_FLOATS * 128 + 4) + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
 #ifndef CTB_DEF_MAX
-#define CTB_DEF_MAX 12
+#define CTB_DEF_MAX 16
 #endif
 constexpr int MV_DEF_MAX = CTB_DEF_MAX;   // most blocks of a mid-row segment whose terms are parked before the state arrives
 #ifndef CTB_RING
