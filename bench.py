@@ -82,10 +82,34 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+        self.index, self.rows, self.stop_flag, self.proc = index, [], threading.Event(), None
 
     def run(self):
-        while not self.stop_flag.is_set():
+        # one long-running nvidia-smi in loop mode (a sample every 50 ms) instead of one process per sample
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"]
+        try:
+            self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+        finally:
+            try:
+                self.proc.kill()
+            except Exception:
+                pass
+
+    def summary(self):
+        self.stop_flag.set()
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+        self.join(timeout=6)
+        if not self.rows:   # loop mode unavailable: one direct query as a last resort
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -93,11 +117,6 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
-
-    def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
