@@ -9,13 +9,16 @@
 //     activation quantization to Q8_K (K-quants) or Q8_0 (Q4_0/Q8_0), bit-exact    k_quants.c:1191-1226, ggml.c:1232-1268
 //   body — the reference's AVX2 kernels restated lane for lane.  Each AVX2 kernel keeps an 8-lane fp32 accumulator in which
 //     lane l holds, per block, (float)(integer dot of elements 4l..4l+3 of every 32-element group, times the sub-block scales)
-//     folded in with ONE fmadd per block, blocks in order, and ends with hsum_float_8.  Here 8 GPU lanes play the 8 AVX lanes
-//     of one weight row, a warp carries 4 rows, dp4a does the 4-element integer dots, and the per-block fmaf chain and the
-//     final shuffle tree reproduce the float order — results equal the reference's bit for bit:
+//     folded in with ONE fmadd per block, blocks in order, and ends with hsum_float_8.  K-quants: 4 GPU lanes share a weight
+//     row (lane u plays AVX lanes u and u+4), a warp carries an 8-row tile, dp4a does the 4-element integer dots, dp2a folds
+//     the 6-bit scales; Q4_0 / Q8_0: 8 lanes per row, 4 rows per warp.  The per-block fmaf chain and the final shuffle tree
+//     reproduce the float order — results equal the reference's bit for bit:
 //     Q4_K k_quants.c:2651-2714 · Q5_K 3174-3262 · Q6_K 3794-3872 · Q4_0 ggml.c:2500-2525 · Q8_0 3379-3402 · F16 2392-2426
+//   scheduling (K-quants) — see k_matvec: contiguous equal block ranges per warp, rows cut between warps are folded in order
+//     by handing the fp32 state from warp to warp through shared memory
 //   epilogue
-//     store | + residual (ggml_add, llama.cpp:2415, 2453) | SiLU-table(gate)·up (ggml.c:3625-3632, llama.cpp:2438-2443)
-//     | GELU-table (falcon, ggml.c:3568-3575)
+//     store | + residual (ggml_add, llama.cpp:2415, 2453) | SiLU table of the gate rows (ggml.c:3625-3632; the product with
+//     up is formed where ffn_down stages its input, llama.cpp:2438-2443) | GELU table (falcon, ggml.c:3568-3575)
 //
 // Why exactness matters: the next mat-mul re-quantizes this output to int8; a 1-ulp difference can flip one rounding and the
 // logits then differ by ~1e-3 (measured).  HBM traffic per launch = the weight planes once + O(K) activations from L2.
