@@ -566,7 +566,7 @@ __device__ __forceinline__ float fold_finish(int type, const Fold& f) {
 // (for the tile its range starts in the middle of) and posts at most one (for the tile its range ends in the middle of).
 constexpr int MV_SMEM_LIMIT = 227 * 1024 / CTB_CTAS_PER_SM - (CTB_CTAS_PER_SM > 1 ? 1024 : 0) - ((MV_WARPS + 1) * (KQ_FOLD_FLOATS * 128 + 4) + MV_WARPS * 8 + 256);   // dynamic shared memory a launch may ask for: 227 KB per CTA minus the static part
 #ifndef CTB_DEF_MAX
-#define CTB_DEF_MAX 16
+#define CTB_DEF_MAX 20
 #endif
 constexpr int MV_DEF_MAX = CTB_DEF_MAX;   // most blocks of a mid-row segment whose terms are parked before the state arrives
 #ifndef CTB_RING
@@ -817,7 +817,7 @@ __host__ __device__ inline int tile_cost(int type) { return type == GT_Q6_K ? 13
 struct TileSpace {
   int tiles[MV_MAX_SEG], cost[MV_MAX_SEG], nseg, ntiles;
   long total;   // Σ tiles·cost
-  __device__ __forceinline__ void init(const MVParams& p) {
+  __host__ __device__ __forceinline__ void init(const MVParams& p) {
     nseg = p.nseg; ntiles = 0; total = 0;
 #pragma unroll
     for (int s = 0; s < MV_MAX_SEG; s++) {
@@ -827,7 +827,7 @@ struct TileSpace {
     }
   }
   // matrix a tile of the concatenated space belongs to; `tile` becomes the tile index inside that matrix
-  __device__ __forceinline__ int locate(int& tile) const {
+  __host__ __device__ __forceinline__ int locate(int& tile) const {
     static_assert(MV_MAX_SEG == 3, "locate() is written out for three segments");
     if (tile < tiles[0]) return 0;
     tile -= tiles[0];
@@ -836,7 +836,7 @@ struct TileSpace {
     return 2;
   }
   // first tile of CTA c of G: the tile at which the cumulative cost reaches c/G of the total
-  __device__ __forceinline__ int boundary(int c, int G) const {
+  __host__ __device__ __forceinline__ int boundary(int c, int G) const {
     if (c >= G) return ntiles;
     long target = total * c / G;
     int base = 0;
@@ -988,8 +988,13 @@ inline MVLaunch matvec_launch_shape(MVParams& p, int n_sm) {
     if (L.attn && L.kt != GT_Q4_K) L.kt = 0;   // the attention tail is instantiated for the Q4_K and the generic kernel only
     L.grid = (int)std::max<long>(1, std::min<long>(units, (long)n_sm * CTB_CTAS_PER_SM));
     const long room = (long)MV_SMEM_LIMIT - (long)act;
-    // a parked (mid-row) segment is never longer than a warp's range nor than a row; shared memory not asked for stays L1
-    const long nb = p.K / 256, tiles_per_cta = (units + L.grid - 1) / L.grid;
+    // a parked (mid-row) segment is never longer than a warp's range nor than a row; shared memory not asked for stays L1.
+    // The range comes from the largest CTA of the actual (cost-balanced) partition.
+    TileSpace ts;
+    ts.init(p);
+    long tiles_per_cta = 1;
+    for (int c = 0; c < L.grid; c++) tiles_per_cta = std::max<long>(tiles_per_cta, ts.boundary(c + 1, L.grid) - ts.boundary(c, L.grid));
+    const long nb = p.K / 256;
     const long range = (tiles_per_cta * nb + MV_WARPS - 1) / MV_WARPS;
     const long need = std::min<long>(range, nb - 1);
     p.def_max = (int)std::max<long>(1, std::min<long>(std::min<long>(MV_DEF_MAX, need), room / (MV_WARPS * KQ_PARK_BYTES)));

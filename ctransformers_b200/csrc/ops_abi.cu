@@ -312,6 +312,23 @@ int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const f
   });
 }
 
+// Host-side view of how a K-quant launch is cut up (no GPU needed): the launch geometry and the first row tile of every CTA.
+int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int n_sm, int* first_tile, int* meta) {
+  if (nseg < 1 || nseg > MV_MAX_SEG || K <= 0 || K % 256 != 0) return -1;
+  MVParams p{};
+  p.K = K; p.nseg = nseg; p.act = ACT_Q8_K;
+  for (int s = 0; s < nseg; s++) {
+    if (!type_is_kquant(types[s]) || rows[s] < 1) return -1;
+    p.seg[s].w.type = types[s]; p.seg[s].w.K = K; p.seg[s].w.M = rows[s]; p.seg[s].w.nb = K / 256;
+  }
+  const MVLaunch L = matvec_launch_shape(p, n_sm);
+  TileSpace ts;
+  ts.init(p);
+  for (int c = 0; c <= L.grid; c++) first_tile[c] = ts.boundary(c, L.grid);
+  meta[0] = L.grid; meta[1] = (int)L.smem; meta[2] = p.def_max; meta[3] = ts.ntiles; meta[4] = MV_WARPS; meta[5] = MV_KQ_ROWS; meta[6] = MV_SMEM_LIMIT;
+  return 0;
+}
+
 int ctb_get_row(int type, const void* table_blocks, int K, int n_rows, int row, float* out) {
   return guarded("ctb_get_row", [&] {
     const size_t rb = raw_row_bytes(type, K);

@@ -115,6 +115,11 @@ int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache
 /* silu(W1 x) * (W3 x) with the fp16 SiLU table (ggml.c:3625-3632) — the fused FFN gate. */
 int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const float* x, float* out, int K, int M);
 /* ggml_get_rows on a quantized table (ggml.c:11615-11642). */
+/* How a K-quant mat-vec launch over nseg matrices (types[], rows[], all K wide) is cut up on a GPU with n_sm SMs — pure host
+ * arithmetic, no device needed: first_tile[0..grid] = first 8-row tile of each CTA (cost-balanced), meta = {grid, dynamic
+ * shared bytes, parked blocks per warp, tiles, warps per CTA, rows per tile, shared-memory limit}.  0 on success. */
+int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int n_sm, int* first_tile, int* meta);
+
 int ctb_get_row(int type, const void* table_blocks, int K, int n_rows, int row, float* out);
 
 #ifdef __cplusplus
