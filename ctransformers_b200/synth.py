@@ -362,3 +362,61 @@ def write_falcon(path, shape: FalconShape = FALCON_7B_SHAPED, ftype="Q5_K_M", se
     mat("output.weight", out_t, E, shape.n_vocab, sigma * 2)
     w.write()
     return dict(path=str(path), weight_bytes_per_token=per_token[0], tensor_types=types_used)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPT-2 in the old GGML ".bin" container (BASELINE.json configs[0]: the reference's own CPU-runnable case; the B200 library
+# does not serve this format — see DESIGN.md §8).  Layout per the reference loader: magic, six int32 hyper-parameters,
+# vocabulary (count, then length-prefixed strings), then tensors {n_dims, name length, type, ne[], name, data}
+# (reference: models/llms/gpt2.cc:60-250).
+@dataclass
+class GPT2Shape:
+    n_vocab: int = 50257
+    n_ctx: int = 1024
+    n_embd: int = 768
+    n_head: int = 12
+    n_layer: int = 12
+
+
+GPT2_117M = GPT2Shape()
+
+
+def write_gpt2_ggml(path, shape: GPT2Shape = GPT2_117M, ftype="Q4_0", seed=0, sigma=0.02):
+    import struct
+    wt = {"Q4_0": Q4_0, "F16": F16, "F32": F32}[ftype]
+    file_ftype = {"F32": 0, "F16": 1, "Q4_0": 2}[ftype] + (2000 if ftype == "Q4_0" else 0)   # GGML_QNT_VERSION 2 * 1000 + ftype
+    rng = np.random.default_rng(seed)
+    E, V, C = shape.n_embd, shape.n_vocab, shape.n_ctx
+    assert E % BLOCK[wt][0] == 0
+
+    def tensor(f, name, t, ne):       # ne[0] is the contiguous dimension
+        rows = int(np.prod(ne[1:])) if len(ne) > 1 else 1
+        if t == F32 and len(ne) == 1:
+            data = (np.ones(ne[0], np.float32) if name.endswith("/g") else (rng.standard_normal(ne[0]) * 0.01).astype(np.float32)).view(np.uint8)
+        else:
+            data = random_blocks(t, ne[0], rows, sigma, rng)
+        nm = name.encode()
+        f.write(struct.pack("<iii", len(ne), len(nm), t))
+        f.write(struct.pack("<" + "i" * len(ne), *ne))
+        f.write(nm)
+        f.write(np.ascontiguousarray(data).tobytes())
+
+    with open(path, "wb") as f:
+        f.write(struct.pack("<I", 0x67676D6C))
+        f.write(struct.pack("<iiiiii", V, C, E, shape.n_head, shape.n_layer, file_ftype))
+        f.write(struct.pack("<i", V))
+        for i in range(V):
+            w = (chr(33 + i) if i < 94 else f"<{i}>").encode()
+            f.write(struct.pack("<I", len(w)))
+            f.write(w)
+        tensor(f, "model/ln_f/g", F32, [E]); tensor(f, "model/ln_f/b", F32, [E])
+        tensor(f, "model/wte", wt, [E, V]); tensor(f, "model/wpe", F32, [E, C])
+        for i in range(shape.n_layer):
+            h = f"model/h{i}/"
+            tensor(f, h + "ln_1/g", F32, [E]); tensor(f, h + "ln_1/b", F32, [E])
+            tensor(f, h + "ln_2/g", F32, [E]); tensor(f, h + "ln_2/b", F32, [E])
+            tensor(f, h + "attn/c_attn/w", wt, [E, 3 * E]); tensor(f, h + "attn/c_attn/b", F32, [3 * E])
+            tensor(f, h + "attn/c_proj/w", wt, [E, E]); tensor(f, h + "attn/c_proj/b", F32, [E])
+            tensor(f, h + "mlp/c_fc/w", wt, [E, 4 * E]); tensor(f, h + "mlp/c_fc/b", F32, [4 * E])
+            tensor(f, h + "mlp/c_proj/w", wt, [4 * E, E]); tensor(f, h + "mlp/c_proj/b", F32, [E])
+    return path
