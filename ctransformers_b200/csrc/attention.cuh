@@ -186,13 +186,18 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
-// DEP = 0: a kernel of its own, q/k/v come from the previous kernel (griddepcontrol.wait).
-// DEP = 1: the tail of the QKV mat-vec launch (matvec.cuh): q/k/v rows come from other CTAs of the SAME launch, which count
-//          their finished row tiles in *dep_counter; the body waits until all dep_target tiles are in.
-template <int DEP>
-__device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, const int h, const int n, const int cg, const int* dep_counter, const int dep_target) {
-  __shared__ float red_f[ATTN_WARPS];
-  __shared__ double red_d[ATTN_WARPS];
+// named barrier over the first NT threads of the CTA (BAR 0 with NT == blockDim.x is __syncthreads)
+template <int BAR, int NT>
+__device__ __forceinline__ void attn_bar() { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); }
+
+// NT threads (barrier BAR) work on one (head, channel group) task.
+// PDLWAIT = true: a kernel of its own, q/k/v come from the previous kernel (griddepcontrol.wait after the prefetches).
+// PDLWAIT = false: a phase of the persistent step kernel (stream.cuh); the caller has already synchronised with the producers.
+template <int NT, int BAR, bool PDLWAIT>
+__device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, const int h, const int n, const int cg) {
+  constexpr int NW = NT / 32;
+  __shared__ float red_f[NW];
+  __shared__ double red_d[NW];
   const int hd = p.hd, per = hd >> 5;
   // Everything up to pdl_wait() reads only what earlier steps left behind (device state, RoPE table, cached K/V rows of
   // older positions): it overlaps the tail of the QKV kernel.  q/k/v of this token are read after the wait.
@@ -214,7 +219,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
 
   const int lim = min(T, n_vec);
   const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
-  constexpr int CPW = ATTN_CH / ATTN_WARPS;             // V channels per warp
+  constexpr int CPW = (ATTN_CH + NW - 1) / NW;          // V channels per warp (the last round may be partial)
   uint4 vpre[CPW][2];                                   // this warp's V rows, first two 256-position chunks
   uint2 kpre[8];                                        // this warp's first 8 K rows (hd == 128)
   float2 cs_pre = make_float2(1.f, 0.f);
@@ -222,7 +227,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
   for (int j = 0; j < CPW; j++)
 #pragma unroll
     for (int ch = 0; ch < 2; ch++)
-      vpre[j][ch] = (ch * 256 < lim) ? *(const uint4*)(vhead + (size_t)(cg * ATTN_CH + warp + j * ATTN_WARPS) * cp + ch * 256 + lane * 8) : make_uint4(0, 0, 0, 0);
+      vpre[j][ch] = (ch * 256 < lim && warp + j * NW < ATTN_CH) ? *(const uint4*)(vhead + (size_t)(cg * ATTN_CH + warp + j * NW) * cp + ch * 256 + lane * 8) : make_uint4(0, 0, 0, 0);
   if (per == 4) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -237,19 +242,14 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
     }
   }
   if (threadIdx.x < hd / 2) cs_pre = p.rope[(size_t)pos * (hd / 2) + threadIdx.x];
-  if (DEP == 0) {
-    pdl_wait();
-  } else {
-    if (threadIdx.x == 0) while (ld_acquire_gpu(dep_counter) < dep_target) { }
-    __syncthreads();
-  }
+  if (PDLWAIT) pdl_wait();
 
   {  // RoPE (pairs) + f16 conversion of q, k, v for this position
     const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
     const float* kv = p.k + (size_t)n * p.kv_stride + (size_t)kvh * hd;
     const float* vv = p.v + (size_t)n * p.kv_stride + (size_t)kvh * hd;
     uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kvh) * hd;
-    for (int i = threadIdx.x; i < hd / 2; i += ATTN_THREADS) {
+    for (int i = threadIdx.x; i < hd / 2; i += NT) {
       const float2 cs = i == (int)threadIdx.x ? cs_pre : p.rope[(size_t)pos * (hd / 2) + i];
       const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
       float o0, o1;
@@ -260,19 +260,19 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
       k16[k_perm(i0, hd)] = h0; k16[k_perm(i1, hd)] = h1;
       if (kv_writer && cg == 0) { kd[k_perm(i0, hd)] = h0; kd[k_perm(i1, hd)] = h1; }
     }
-    for (int c = threadIdx.x; c < hd; c += ATTN_THREADS) {
+    for (int c = threadIdx.x; c < hd; c += NT) {
       const uint16_t hv = f2h(__ldcg(vv + c));
       v16[c] = hv;
       if (kv_writer && c / ATTN_CH == cg) p.vc[((size_t)kvh * hd + c) * cp + v_perm(pos)] = hv;
     }
   }
-  __syncthreads();
+  attn_bar<BAR, NT>();
 
   if (per == 4) {
     // 8 cached rows per warp step, all loads issued before the first is used (the loop is latency-bound otherwise)
     const uint2 qq = *(const uint2*)(q16 + lane * 4);
     const float q0 = h2f((uint16_t)(qq.x & 0xffff)), q1 = h2f((uint16_t)(qq.x >> 16)), q2 = h2f((uint16_t)(qq.y & 0xffff)), q3 = h2f((uint16_t)(qq.y >> 16));
-    for (int t0 = warp * 8; t0 < T; t0 += ATTN_WARPS * 8) {
+    for (int t0 = warp * 8; t0 < T; t0 += NW * 8) {
       uint2 kk[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -296,7 +296,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
     // head_dim 64 (Falcon): the same 8-rows-in-flight scheme with 4-byte row pieces
     const uint32_t qq = *(const uint32_t*)(q16 + lane * 2);
     const float q0 = h2f((uint16_t)(qq & 0xffff)), q1 = h2f((uint16_t)(qq >> 16));
-    for (int t0 = warp * 8; t0 < T; t0 += ATTN_WARPS * 8) {
+    for (int t0 = warp * 8; t0 < T; t0 += NW * 8) {
       uint32_t kk[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -315,7 +315,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
       }
     }
   } else {
-    for (int t = warp; t < T; t += ATTN_WARPS) {
+    for (int t = warp; t < T; t += NW) {
       const uint16_t* kr = (t == pos) ? (k16 + lane * per) : (p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * per);
       float s = 0.f;
       for (int i = 0; i < per; i++) s = __fmaf_rn(h2f(kr[i]), h2f(q16[lane * per + i]), s);
@@ -323,32 +323,32 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
       if (lane == 0) sc[t] = __fmul_rn(s, p.kq_scale);
     }
   }
-  __syncthreads();
+  attn_bar<BAR, NT>();
 
   float mx = -INFINITY;
-  for (int t = threadIdx.x; t < T; t += ATTN_THREADS) mx = fmaxf(mx, sc[t]);
+  for (int t = threadIdx.x; t < T; t += NT) mx = fmaxf(mx, sc[t]);
   mx = warp_max(mx);
   if (lane == 0) red_f[warp] = mx;
-  __syncthreads();
+  attn_bar<BAR, NT>();
   mx = red_f[0];
 #pragma unroll
-  for (int w = 1; w < ATTN_WARPS; w++) mx = fmaxf(mx, red_f[w]);
+  for (int w = 1; w < NW; w++) mx = fmaxf(mx, red_f[w]);
   double sum = 0.0;
-  for (int t = threadIdx.x; t < T; t += ATTN_THREADS) {
+  for (int t = threadIdx.x; t < T; t += NT) {
     const float val = h2f(__ldg(p.exp_tab + f2h(__fsub_rn(sc[t], mx))));
     sc[t] = val;
     sum += (double)val;
   }
   sum = warp_sum(sum);
   if (lane == 0) red_d[warp] = sum;
-  __syncthreads();
+  attn_bar<BAR, NT>();
   sum = 0.0;
 #pragma unroll
-  for (int w = 0; w < ATTN_WARPS; w++) sum += red_d[w];
+  for (int w = 0; w < NW; w++) sum += red_d[w];
   const float inv = (float)(1.0 / sum);
   const int t_end = (T + 255) & ~255;
-  for (int t = threadIdx.x; t < t_end; t += ATTN_THREADS) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
-  __syncthreads();
+  for (int t = threadIdx.x; t < t_end; t += NT) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
+  attn_bar<BAR, NT>();
 
   // V·P for this CTA's channels.  lane part: positions t < min(T, n_vec); lane L takes t = 32i+L in increasing i.
   // leftover part (ggml.c:2415-2418): positions n_vec <= t < T are added one by one in double after the lane reduction.  They
@@ -358,7 +358,8 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
   const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
 #pragma unroll
   for (int j = 0; j < CPW; j++) {
-    const int cc = warp + j * ATTN_WARPS;
+    const int cc = warp + j * NW;
+    if (cc >= ATTN_CH) break;
     const int c = cg * ATTN_CH + cc;
     const uint16_t* vrow = vhead + (size_t)c * cp;
     const uint16_t vcur = v16[c];
@@ -398,7 +399,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
 static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_trigger();
-  attn_body<0>(p, smem, blockIdx.x, blockIdx.y, blockIdx.z, nullptr, 0);
+  attn_body<ATTN_THREADS, 0, true>(p, smem, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // ----------------------------------------------------------------------------------------- argmax

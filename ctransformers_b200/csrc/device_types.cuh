@@ -1,22 +1,21 @@
 // Device-side data layout of the quantized hot path (sm_100a).
 //
 // Weights are NOT kept in GGUF's array-of-blocks form.  At load time every 2-D weight is repacked,
-// byte for byte (same total size, so the HBM roofline denominator is unchanged), into per-tensor
-// planes so that every lane of a warp issues 16-byte, 16-byte-aligned, fully coalesced loads no
-// matter how odd the source block size is (Q6_K = 210 B, Q4_0 = 18 B, Q8_0 = 34 B):
+// byte for byte (same total size, so the HBM roofline denominator is unchanged):
+//   K-quants (Q4_K / Q5_K / Q6_K): the STREAM layout of stream.cuh — 16-row tiles, block-major, every (tile, block) a
+//   contiguous 16-byte-aligned piece of 16 x {144,176,210} bytes that one cp.async.bulk moves into shared memory and whose
+//   interior is ordered for conflict-free 16-byte shared-memory loads of the mma.sync operand fragments.
+//   Other types: per-tensor planes so that every lane of a warp issues 16-byte-aligned, fully coalesced loads no
+//   matter how odd the source block size is (Q4_0 = 18 B, Q8_0 = 34 B):
 //
 //   type   plane qs (per row)          plane qh (per row)   plane sc (per row)               plane d (per row)
-//   Q4_K   nb x 128 B nibbles          -                    nb x 16 B {d,dmin,scales[12]}     -
-//   Q5_K   nb x 128 B nibbles          nb x 32 B high bits  nb x 16 B {d,dmin,scales[12]}     -
-//   Q6_K   nb x 128 B ql               nb x 64 B qh         nb x 16 B int8 scales             nb x fp16
 //   Q4_0   nb x 16 B nibbles           -                    -                                 nb x fp16
 //   Q8_0   nb x 32 B int8              -                    -                                 nb x fp16
 //   F16    K x 2 B                     -                    -                                 -
 //   F32    K x 4 B                     -                    -                                 -
 //
 // Block contents are exactly the reference's (k_quants.h:76-117, ggml.c:888-925); only their placement
-// changes.  Inside each K-quant block the 32-bit words of qs/qh are additionally stored lane-major
-// (repack.cuh) so that the GPU lane that plays AVX2 lane l fetches all its words with one 16-byte load.  Activations are quantized on the fly to the reference's Q8_K / Q8_0 (bit-exact) into
+// changes.  Activations are quantized on the fly to the reference's Q8_K / Q8_0 (bit-exact) into
 // shared memory (struct ActView) and never touch HBM.
 #pragma once
 #include <cstdint>
@@ -35,6 +34,7 @@ struct DevMat {
   const uint8_t* qh = nullptr;
   const uint8_t* sc = nullptr;
   const uint16_t* d = nullptr;
+  const uint8_t* st = nullptr;   // K-quants: the stream layout of stream.cuh (16-row tiles, block-major; qs/qh/sc/d stay null)
   size_t bytes = 0;     // total bytes of all planes (= GGUF tensor bytes)
 };
 

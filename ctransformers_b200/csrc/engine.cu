@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "repack.cuh"
+#include "stream.cuh"
 #include "tables.hpp"
 
 namespace ctb {
@@ -22,6 +23,13 @@ namespace ctb {
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// one op of the per-token schedule: a phase of the step kernel, or (mat-vecs over non-K-quant weights) a kernel of its own
+struct StepOp {
+  Phase ph;
+  int mvk = 0;          // PH_MATVEC: which projection (MVK_*)
+  bool stream = false;  // PH_MATVEC: runs inside the step kernel
+};
 
 // advance the on-device decode state after a greedy pick: state = {token, n_past, step}
 // state = {token, position, step, n_total}; pick lives in state[4]
@@ -46,7 +54,10 @@ static size_t max_raw_tensor_bytes(const GGUFFile& g) {
 
 size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   size_t total = 0;
-  for (const auto& t : g.tensors) total += align_up(t.nbytes, 256) + 4 * 256;   // up to 4 planes, each 256-aligned
+  for (const auto& t : g.tensors) {
+    total += align_up(t.nbytes, 256) + 4 * 256;   // up to 4 planes, each 256-aligned
+    if (t.ne[1] > 0) total += align_up(t.nbytes / (size_t)t.ne[1] * ST_ROWS, 256);   // K-quants: rows padded to whole 16-row tiles
+  }
   total += align_up(max_raw_tensor_bytes(g), 256);                              // raw staging for the repack
   const size_t kv = (size_t)hp.n_layer * (hp.n_ctx + 256) * hp.n_embd_gqa() * 2;
   total += 2 * align_up(kv, 256);
@@ -54,6 +65,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
   total += 4 * (2 * (size_t)hp.n_embd + qkv + 3 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + (size_t)hp.n_vocab) + 64 * 256;
+  total += ((size_t)hp.n_layer * 8 + 8) * sizeof(Phase) * 2 + 4096;   // the step programs
   total += 1 << 20;
   return total;
 }
@@ -65,21 +77,35 @@ void* Engine::alloc(size_t bytes, size_t align) {
   return arena_ + off;
 }
 
-DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging) {
+DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging, int want_K, int want_M) {
   if (!supported_matrix_type(t.type)) throw std::runtime_error("tensor '" + t.name + "': quantization type " + std::to_string(t.type) + " is not supported by the B200 path");
   DevMat m;
   m.type = (int)t.type;
   m.K = (int)t.ne[0];
   m.M = (int)(t.ne[1] * t.ne[2] * t.ne[3]);
+  // the reference rejects a tensor whose shape does not follow from the hyper-parameters (llama.cpp:1345-1361 "wrong shape")
+  if (m.K != want_K || m.M != want_M)
+    throw std::runtime_error("tensor '" + t.name + "' has wrong shape; expected " + std::to_string(want_K) + " x " + std::to_string(want_M) + ", got " +
+                             std::to_string(m.K) + " x " + std::to_string(m.M));
   m.nb = m.K / type_block_elems(t.type);
   m.bytes = t.nbytes;
+  CTB_CUDA(cudaMemcpyAsync(staging, t.data, t.nbytes, cudaMemcpyHostToDevice, stream_));
+  if (type_is_kquant(m.type)) {
+    const size_t sb = st_matrix_bytes(m.type, m.M, m.nb);
+    uint16_t* st = (uint16_t*)alloc(sb);
+    const int grid = (int)std::min<size_t>((sb / 2 + 255) / 256, (size_t)sm_count_ * 32);
+    k_repack_stream<<<grid, 256, 0, stream_>>>(m.type, staging, m.M, m.nb, st);
+    CTB_CUDA(cudaGetLastError());
+    CTB_CUDA(cudaStreamSynchronize(stream_));   // staging is reused by the next tensor
+    m.st = (const uint8_t*)st;
+    return m;
+  }
   uint16_t *qs = nullptr, *qh = nullptr, *sc = nullptr, *d = nullptr;
   const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, t.nbytes);
   qs = (uint16_t*)alloc(ps.qs);
   if (ps.qh) qh = (uint16_t*)alloc(ps.qh);
   if (ps.sc) sc = (uint16_t*)alloc(ps.sc);
   if (ps.d) d = (uint16_t*)alloc(ps.d);
-  CTB_CUDA(cudaMemcpyAsync(staging, t.data, t.nbytes, cudaMemcpyHostToDevice, stream_));
   const size_t n_u16 = t.nbytes / 2;
   const int grid = (int)std::min<size_t>((n_u16 + 255) / 256, (size_t)sm_count_ * 32);
   k_repack<<<grid, 256, 0, stream_>>>(m.type, (const uint16_t*)staging, n_u16, qs, qh, sc, d);
@@ -89,13 +115,14 @@ DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging) {
   return m;
 }
 
-const float* Engine::upload_vector(const GGUFFile& g, const std::string& name, bool required) {
+const float* Engine::upload_vector(const GGUFFile& g, const std::string& name, bool required, int want_n) {
   const GGUFTensor* t = g.tensor(name);
   if (!t) {
     if (required) throw std::runtime_error("tensor '" + name + "' not found");
     return nullptr;
   }
   if (t->type != T_F32) throw std::runtime_error("tensor '" + name + "' must be f32");
+  if ((long)t->ne[0] * (long)t->ne[1] != (long)want_n) throw std::runtime_error("tensor '" + name + "' has wrong shape");
   float* d = (float*)alloc(t->nbytes);
   CTB_CUDA(cudaMemcpy(d, t->data, t->nbytes, cudaMemcpyHostToDevice));
   return d;
@@ -132,10 +159,24 @@ static inline uint16_t host_f2h(float f) {
 }
 
 Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), device_(device) {
+  // everything acquired below is released by release() if the constructor throws (the destructor does not run then)
+  try {
+    init(g);
+  } catch (...) {
+    release();
+    throw;
+  }
+}
+
+void Engine::init(const GGUFFile& g) {
   CTB_CUDA(cudaSetDevice(device_));
   cudaDeviceProp prop;
   CTB_CUDA(cudaGetDeviceProperties(&prop, device_));
   sm_count_ = prop.multiProcessorCount;
+  // refuse what the kernels cannot run BEFORE the model-sized allocations are made
+  for (const auto& t : g.tensors)
+    if (t.n_dims >= 2 && !supported_matrix_type(t.type))
+      throw std::runtime_error("tensor '" + t.name + "': quantization type " + std::to_string(t.type) + " is not supported by the B200 path");
   CTB_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   CTB_CUDA(cudaEventCreate(&ev0_));
   CTB_CUDA(cudaEventCreate(&ev1_));
@@ -144,44 +185,45 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   CTB_CUDA(cudaMalloc(&arena_, arena_size_));
   uint8_t* staging = (uint8_t*)alloc(align_up(max_raw_tensor_bytes(g), 256));
 
-  // ---- weights
+  // ---- weights (shapes follow from the hyper-parameters: llama.cpp:1878-1934 llama, 1948-2012 falcon)
   const std::string pfx = "blk.";
+  const int n_embd = hp_.n_embd, gqa = hp_.n_embd_gqa(), n_ff = hp_.n_ff;
   {
     const GGUFTensor& te = g.need_tensor("token_embd.weight");
     if (!supported_matrix_type(te.type)) throw std::runtime_error("token_embd.weight: unsupported type");
+    if ((int)te.ne[0] != n_embd || (long)(te.ne[1] * te.ne[2] * te.ne[3]) != (long)hp_.n_vocab) throw std::runtime_error("token_embd.weight has wrong shape");
     uint8_t* d = (uint8_t*)alloc(te.nbytes);
     CTB_CUDA(cudaMemcpy(d, te.data, te.nbytes, cudaMemcpyHostToDevice));
     tok_embd_ = d; tok_type_ = (int)te.type;
     tok_row_bytes_ = te.ne[0] / type_block_elems(te.type) * type_block_bytes(te.type);
-    if ((int)te.ne[0] != hp_.n_embd) throw std::runtime_error("token_embd.weight has wrong shape");
   }
-  out_norm_ = upload_vector(g, "output_norm.weight", true);
-  out_norm_b_ = upload_vector(g, "output_norm.bias", hp_.falcon);
-  output_ = upload_matrix(g.need_tensor("output.weight"), staging);
+  out_norm_ = upload_vector(g, "output_norm.weight", true, n_embd);
+  out_norm_b_ = upload_vector(g, "output_norm.bias", hp_.falcon, n_embd);
+  output_ = upload_matrix(g.need_tensor("output.weight"), staging, n_embd, hp_.n_vocab);
   size_t wbytes = output_.bytes;
   layers_.resize(hp_.n_layer);
   for (int il = 0; il < hp_.n_layer; il++) {
     LayerW& L = layers_[il];
     const std::string b = pfx + std::to_string(il) + ".";
-    L.attn_norm = upload_vector(g, b + "attn_norm.weight", true);
+    L.attn_norm = upload_vector(g, b + "attn_norm.weight", true, n_embd);
     if (hp_.falcon) {
-      L.attn_norm_b = upload_vector(g, b + "attn_norm.bias", true);
-      L.attn_norm2 = upload_vector(g, b + "attn_norm_2.weight", false);
-      if (L.attn_norm2) L.attn_norm2_b = upload_vector(g, b + "attn_norm_2.bias", true);
-      L.wqkv = upload_matrix(g.need_tensor(b + "attn_qkv.weight"), staging);
-      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging);
-      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging);
-      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging);
+      L.attn_norm_b = upload_vector(g, b + "attn_norm.bias", true, n_embd);
+      L.attn_norm2 = upload_vector(g, b + "attn_norm_2.weight", false, n_embd);
+      if (L.attn_norm2) L.attn_norm2_b = upload_vector(g, b + "attn_norm_2.bias", true, n_embd);
+      L.wqkv = upload_matrix(g.need_tensor(b + "attn_qkv.weight"), staging, n_embd, n_embd + 2 * gqa);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging, n_embd, n_embd);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging, n_embd, n_ff);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging, n_ff, n_embd);
       wbytes += L.wqkv.bytes + L.wo.bytes + L.w3.bytes + L.w2.bytes;
     } else {
-      L.ffn_norm = upload_vector(g, b + "ffn_norm.weight", true);
-      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), staging);
-      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), staging);
-      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), staging);
-      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging);
-      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), staging);
-      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging);
-      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging);
+      L.ffn_norm = upload_vector(g, b + "ffn_norm.weight", true, n_embd);
+      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), staging, n_embd, n_embd);
+      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), staging, n_embd, gqa);
+      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), staging, n_embd, gqa);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging, n_embd, n_embd);
+      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), staging, n_embd, n_ff);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging, n_ff, n_embd);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging, n_embd, n_ff);
       wbytes += L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.w1.bytes + L.w2.bytes + L.w3.bytes;
       if (act_format_for(L.w1.type) != act_format_for(L.w3.type)) throw std::runtime_error("ffn_gate / ffn_up use incompatible quantization families");
     }
@@ -233,8 +275,9 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
   ffn2_ = (float*)alloc((size_t)hp_.n_ff * 4);
   d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
   d_embd_ = (float*)alloc(hp_.n_embd * 4);
-  attn_cnt_ = (int*)alloc((size_t)hp_.n_layer * 4);
+  d_sync_ = (unsigned*)alloc(64);
   CTB_CUDA(cudaMemset(d_state_, 0, 64));
+  CTB_CUDA(cudaMemset(d_sync_, 0, 64));
   CTB_CUDA(cudaMallocHost(&h_logits_, (size_t)hp_.n_vocab * 4));
   CTB_CUDA(cudaMallocHost(&h_embd_, (size_t)hp_.n_embd * 4));
   memset(h_logits_, 0, (size_t)hp_.n_vocab * 4);
@@ -242,16 +285,17 @@ Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), devi
 
   if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
   if (const char* e = getenv("CTB_NO_SPEC")) spec_on_ = !(e[0] == '1');
-  if (const char* e = getenv("CTB_FUSED_ATTN")) fuse_attn_ = e[0] == '1';
+  if (const char* e = getenv("CTB_STEP_FUSE")) fused_ = !(e[0] == '0');
   CTB_CUDA(cudaMallocHost(&h_spec_tok_, 16));
   CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
+  build_ops();
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();
 }
 
-Engine::~Engine() {
+void Engine::release() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   destroy_graphs();
@@ -266,39 +310,16 @@ Engine::~Engine() {
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
+  h_logits_ = h_embd_ = nullptr; h_state_ = nullptr; h_tokens_out_ = nullptr; d_tokens_out_ = nullptr; arena_ = nullptr; h_spec_tok_ = nullptr;
+  ev_pick_ = ev0_ = ev1_ = nullptr; stream_ = nullptr;
 }
+
+Engine::~Engine() { release(); }
 
 void Engine::set_stream(cudaStream_t s) {
   if (own_stream_ && stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
   stream_ = s;
   own_stream_ = false;
-}
-
-void Engine::launch_attn(const AttnParams& ap) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(hp_.n_head, 1, hp_.head_dim() / ATTN_CH); cfg.blockDim = dim3(ATTN_THREADS);
-  cfg.dynamicSmemBytes = attn_smem_bytes(hp_.n_ctx, hp_.head_dim()); cfg.stream = stream_;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_ ? 1 : 0;
-  CTB_CUDA(cudaLaunchKernelEx(&cfg, k_attn, ap));
-}
-
-void Engine::launch_matvec(MVParams& p, int kind) {
-  if (matvec_only_ && !((matvec_mask_ >> kind) & 1)) return;
-  if (trace_buf_) {
-    p.trace = trace_buf_ + (size_t)trace_launch_ * sm_count_ * (4 + MV_WARPS);
-    trace_kind_.push_back(kind);
-    trace_launch_++;
-  }
-  p.silu_tab = silu_tab_;
-  p.gelu_tab = gelu_tab_;
-  const MVLaunch L = matvec_launch_shape(p, sm_count_);
-  CTB_CUDA(launch_matvec_kernel(L, stream_, p, pdl_));
-  launches_per_step_++;
-  matvec_launches_++;
-  mark(0);
 }
 
 static MVSeg seg(const DevMat& w, float* out, int epi = EPI_STORE, const float* res = nullptr, const float* res2 = nullptr) {
@@ -307,29 +328,48 @@ static MVSeg seg(const DevMat& w, float* out, int epi = EPI_STORE, const float* 
   return s;
 }
 
-// One token through the whole model.  Reads {token, n_past} from d_state_.
-void Engine::enqueue_step(bool with_logits, bool greedy) {
+// The op list of one token through the whole model (the reference rebuilds this graph on every eval, llama.cpp:2872-2876;
+// here it is a static schedule whose pointers never change): EMBED, per layer {QKV mat-vec(s), ATTN, WO, UP, DOWN}, then the
+// HEAD mat-vec and the greedy PICK.  {token, n_past} are read from d_state_ on the device.
+void Engine::push_matvec(MVParams& p, int kind) {
+  p.silu_tab = silu_tab_;
+  p.gelu_tab = gelu_tab_;
+  StepOp op{};
+  op.ph = step_supports(p) ? matvec_phase(p) : Phase{};
+  op.ph.kind = PH_MATVEC;
+  op.ph.mv = p;
+  op.mvk = kind;
+  op.stream = step_supports(p);
+  if (op.stream) op.ph.mv.act = ACT_Q8_K;
+  ops_.push_back(op);
+}
+
+void Engine::build_ops() {
   const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = hp_.n_head_kv, gqa = hp_.n_embd_gqa();
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
-  launches_per_step_ = 0;
-  matvec_launches_ = 0;
-  CTB_CUDA(cudaMemsetAsync(attn_cnt_, 0, (size_t)hp_.n_layer * 4, stream_));   // finished-tile counters of the fused QKV+attention launches
-  mark(-1);
-  if (!matvec_only_) {
-    k_embed<<<1, 256, 0, stream_>>>(tok_embd_, tok_type_, tok_row_bytes_, n_embd, hp_.n_vocab, d_state_, xa_);
-    launches_per_step_++;
+  ops_.clear();
+  {
+    StepOp op{};
+    op.ph.kind = PH_EMBED;
+    op.ph.em.table = tok_embd_; op.ph.em.row_bytes = tok_row_bytes_; op.ph.em.tokens = d_state_; op.ph.em.out = xa_;
+    op.ph.em.type = tok_type_; op.ph.em.K = n_embd; op.ph.em.n_vocab = hp_.n_vocab;
+    ops_.push_back(op);
   }
-  mark(3);
   float* x = xa_;
   float* y = xb_;
   for (int il = 0; il < hp_.n_layer; il++) {
     const LayerW& L = layers_[il];
     uint16_t* kc = kc_ + (size_t)il * hp_.n_ctx * gqa;
     uint16_t* vc = vc_ + (size_t)il * gqa * kv_ctx_pad(hp_.n_ctx);
-    bool attn_fused = false;
     AttnParams ap{};
     ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.state = d_state_; ap.kq_scale = kq_scale;
     ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx; ap.rope = rope_; ap.neox = hp_.falcon ? 1 : 0;
+    auto push_attn = [&]() {
+      StepOp op{};
+      op.ph.kind = PH_ATTN;
+      op.ph.at = ap;
+      ops_.push_back(op);
+    };
 
     if (!hp_.falcon) {
       float* q = qkv_; float* k = qkv_ + n_embd; float* v = qkv_ + n_embd + gqa;
@@ -345,19 +385,15 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
           p.act = act_format_for(ws[i]->type); p.nseg = 0;
           for (int j = i; j < 3; j++)
             if (!done[j] && act_format_for(ws[j]->type) == p.act) { p.seg[p.nseg++] = seg(*ws[j], outs[j]); done[j] = true; }
-          // all of q, k, v in one K-quant launch: attention runs as that launch's tail (no kernel boundary in between)
-          attn_fused = fuse_attn_ && !matvec_only_ && !profiling_ && p.nseg == 3 && type_is_kquant(ws[0]->type);
-          if (attn_fused) { p.attn_on = 1; p.attn = ap; p.attn_counter = attn_cnt_ + il; }
-          launch_matvec(p, MVK_QKV);
+          push_matvec(p, MVK_QKV);
         }
       }
-      if (!matvec_only_ && !attn_fused) { launch_attn(ap); launches_per_step_ += 1; }
-      mark(1);
+      push_attn();
       {  // wo + residual
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
         p.seg[0] = seg(L.wo, y, EPI_ADD, x);
-        launch_matvec(p, MVK_WO);
+        push_matvec(p, MVK_WO);
       }
       {  // ffn_norm + gate and up projections as two independent row sets: silu(gate) is stored, the product with up is formed
          // where ffn_down stages its input
@@ -365,13 +401,13 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
         p.act = act_format_for(L.w1.type); p.nseg = 2;
         p.seg[0] = seg(L.w1, ffn_, EPI_SILU); p.seg[1] = seg(L.w3, ffn2_);
-        launch_matvec(p, MVK_UP);
+        push_matvec(p, MVK_UP);
       }
       {  // w2 on silu(gate)*up, + residual
         MVParams p{};
         p.x = ffn_; p.x2 = ffn2_; p.x_mode = 1; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, x, EPI_ADD, y);
-        launch_matvec(p, MVK_DOWN);
+        push_matvec(p, MVK_DOWN);
       }
       // x now holds the next layer's input
     } else {
@@ -387,45 +423,122 @@ void Engine::enqueue_step(bool with_logits, bool greedy) {
         p.seg[0] = seg(L.wqkv, qkv_);
         if (fuse) { p.seg[1] = seg(L.w3, ffn_, EPI_GELU); p.nseg = 2; }
         ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qkv_w; ap.kv_stride = qkv_w;
-        attn_fused = fuse_attn_ && !matvec_only_ && !profiling_ && type_is_kquant(L.wqkv.type) && (!fuse || type_is_kquant(L.w3.type));
-        if (attn_fused) { p.attn_on = 1; p.attn = ap; p.attn_counter = attn_cnt_ + il; }
-        launch_matvec(p, MVK_QKV);
+        push_matvec(p, MVK_QKV);
       }
       if (!fuse) {
         MVParams p{};
         p.x = x; p.norm_mode = NORM_LAYER; p.eps = hp_.eps; p.K = n_embd; p.norm_w = L.attn_norm; p.norm_b = L.attn_norm_b;
         p.act = act_format_for(L.w3.type); p.nseg = 1;
         p.seg[0] = seg(L.w3, ffn_, EPI_GELU);
-        launch_matvec(p, MVK_UP);
+        push_matvec(p, MVK_UP);
       }
-      if (!matvec_only_ && !attn_fused) { launch_attn(ap); launches_per_step_ += 1; }
-      mark(1);
+      push_attn();
       {  // attention output projection
         MVParams p{};
         p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
         p.seg[0] = seg(L.wo, attn_o_);
-        launch_matvec(p, MVK_WO);
+        push_matvec(p, MVK_WO);
       }
       {  // ffn_down, then + attn_out, then + layer input (llama.cpp:2767-2771 order)
         MVParams p{};
         p.x = ffn_; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
         p.seg[0] = seg(L.w2, y, EPI_ADD2, attn_o_, x);
-        launch_matvec(p, MVK_DOWN);
+        push_matvec(p, MVK_DOWN);
       }
       std::swap(x, y);
     }
   }
-  if (with_logits) {
+  n_body_ = (int)ops_.size();
+  {
     MVParams p{};
     p.x = x; p.norm_w = out_norm_; p.norm_b = out_norm_b_; p.norm_mode = hp_.falcon ? NORM_LAYER : NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
     p.norm_out = d_embd_; p.act = act_format_for(output_.type); p.nseg = 1;
     p.seg[0] = seg(output_, d_logits_);
-    launch_matvec(p, MVK_OUT);
-    if (greedy && !matvec_only_) {
-      k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
-      k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
-      launches_per_step_ += 2;
+    push_matvec(p, MVK_OUT);
+  }
+  {
+    StepOp op{};
+    op.ph.kind = PH_PICK;
+    op.ph.pk.logits = d_logits_; op.ph.pk.state = d_state_; op.ph.pk.out_tokens = nullptr; op.ph.pk.n = hp_.n_vocab;   // out_tokens: set in build_graphs
+    ops_.push_back(op);
+  }
+  // ---- the step kernel's shared-memory shape: ring slots fill what the largest activation image leaves
+  bool any_stream = false;
+  for (const StepOp& op : ops_) any_stream |= op.ph.kind == PH_MATVEC && op.stream;
+  std::vector<Phase> phs;
+  for (const StepOp& op : ops_) if (op.ph.kind != PH_MATVEC || op.stream) phs.push_back(op.ph);
+  const StepLaunch sl = step_launch_shape(phs.data(), (int)phs.size(), sm_count_, step_max_dyn_smem());
+  step_grid_ = sl.grid; step_slots_ = sl.n_slots; step_smem_ = sl.smem;
+  if (any_stream && step_slots_ < 2) throw std::runtime_error("model rows are too long for the step kernel's shared memory");
+  if (any_stream) CTB_CUDA(step_set_smem_limit(step_smem_));
+  else fused_ = false;
+  d_prog_ = (Phase*)alloc((ops_.size() + 1) * sizeof(Phase), 256);
+  d_prog_mv_ = (Phase*)alloc((ops_.size() + 1) * sizeof(Phase), 256);
+}
+
+void Engine::upload_prog(Phase* dst, const std::vector<StepOp>& ops) {
+  std::vector<Phase> phs(ops.size());
+  for (size_t i = 0; i < ops.size(); i++) phs[i] = ops[i].ph;
+  CTB_CUDA(cudaMemcpy(dst, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+}
+
+// Enqueue ops[0, n) on stream_.  Fused mode: maximal runs of ops the step kernel can take become ONE k_step launch (a
+// K-quant model: the whole token); anything else (Q4_0 / Q8_0 / F16 / F32 mat-vecs) runs as its own kernel.  Un-fused mode
+// (CTB_STEP_FUSE=0): one kernel per op, K-quant mat-vecs as one-phase k_step launches.
+void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n) {
+  launches_per_step_ = 0;
+  StepLaunch step_shape_;
+  step_shape_.grid = step_grid_; step_shape_.n_slots = step_slots_; step_shape_.smem = step_smem_;
+  auto capable = [&](const StepOp& op) { return op.ph.kind != PH_MATVEC || op.stream; };
+  int i = 0;
+  while (i < n) {
+    const StepOp& op = ops[i];
+    if (fused_ && capable(op)) {
+      int j = i;
+      while (j < n && capable(ops[j])) j++;
+      mark(-1);
+      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, j - i, d_sync_, pdl_));
+      launches_per_step_++;
+      mark(0);
+      i = j;
+      continue;
     }
+    mark(-1);
+    switch (op.ph.kind) {
+      case PH_EMBED:
+        k_embed<<<1, 256, 0, stream_>>>(op.ph.em.table, op.ph.em.type, op.ph.em.row_bytes, op.ph.em.K, op.ph.em.n_vocab, op.ph.em.tokens, op.ph.em.out);
+        launches_per_step_++;
+        mark(3);
+        break;
+      case PH_ATTN: {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(hp_.n_head, 1, hp_.head_dim() / ATTN_CH); cfg.blockDim = dim3(ATTN_THREADS);
+        cfg.dynamicSmemBytes = attn_smem_bytes(hp_.n_ctx, hp_.head_dim()); cfg.stream = stream_;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = pdl_ ? 1 : 0;
+        CTB_CUDA(cudaLaunchKernelEx(&cfg, k_attn, op.ph.at));
+        launches_per_step_++;
+        mark(1);
+      } break;
+      case PH_PICK:
+        k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
+        k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
+        launches_per_step_ += 2;
+        mark(3);
+        break;
+      default:
+        if (op.stream) {
+          CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, 1, d_sync_, pdl_));
+        } else {
+          const MVLaunch L = matvec_launch_shape(op.ph.mv, sm_count_);
+          CTB_CUDA(launch_matvec_kernel(L, stream_, op.ph.mv, pdl_));
+        }
+        launches_per_step_++;
+        mark(0);
+    }
+    i++;
   }
   CTB_CUDA(cudaGetLastError());
 }
@@ -439,6 +552,7 @@ void Engine::mark(int kind) {
   prof_kind_.push_back(kind);
 }
 
+// One eager decode step, one kernel per op (un-fused), a CUDA event around every kernel: the kernel classes' share of a step.
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
   CTB_CUDA(cudaSetDevice(device_));
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
@@ -446,9 +560,10 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
   h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
   const long keep = launches_per_step_;
-  profiling_ = true;
-  try { enqueue_step(true, false); } catch (...) { profiling_ = false; throw; }
-  profiling_ = false;
+  const bool keep_fused = fused_;
+  profiling_ = true; fused_ = false;
+  try { enqueue_ops(ops_, d_prog_, n_body_ + 1); } catch (...) { profiling_ = false; fused_ = keep_fused; throw; }
+  profiling_ = false; fused_ = keep_fused;
   launches_per_step_ = keep;
   CTB_CUDA(cudaStreamSynchronize(stream_));
   int n = 0;
@@ -463,75 +578,33 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
   return n;
 }
 
-// One decode step replayed as a CUDA graph in which every k_matvec CTA stamps %globaltimer at entry, when its dependency is
-// released, when its input is staged and when each warp finishes: the in-graph anatomy of the per-launch fixed cost.
-// out: per launch {kind, grid, then per CTA (4 + MV_WARPS) stamps}; returns the number of launches, or -needed-size.
-long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
-  CTB_CUDA(cudaSetDevice(device_));
-  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
-  const size_t per_launch = (size_t)sm_count_ * (4 + MV_WARPS);
-  const size_t max_launches = (size_t)hp_.n_layer * 5 + 2;
-  unsigned long long* buf = nullptr;
-  CTB_CUDA(cudaMalloc(&buf, max_launches * per_launch * 8));
-  CTB_CUDA(cudaMemset(buf, 0, max_launches * per_launch * 8));
-  cudaStream_t user = stream_, cap;
-  CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-  const long keep = launches_per_step_;
-  cudaGraphExec_t ex = nullptr;
-  stream_ = cap; trace_buf_ = buf; trace_launch_ = 0; trace_kind_.clear();
-  try {
-    cudaGraph_t g;
-    CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_step(true, false);
-    CTB_CUDA(cudaStreamEndCapture(cap, &g));
-    CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
-    cudaGraphDestroy(g);
-  } catch (...) { stream_ = user; trace_buf_ = nullptr; launches_per_step_ = keep; cudaStreamDestroy(cap); cudaFree(buf); throw; }
-  stream_ = user; trace_buf_ = nullptr; launches_per_step_ = keep;
-  cudaStreamDestroy(cap);
-  const long n = trace_launch_;
-  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
-  for (int rep = 0; rep < 3; rep++) {      // the last replay is the one read back (warm)
-    h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
-    CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
-    CTB_CUDA(cudaGraphLaunch(ex, stream_));
-    CTB_CUDA(cudaStreamSynchronize(stream_));
-  }
-  cudaGraphExecDestroy(ex);
-  const long need = n * (long)(2 + per_launch);
-  if (need > cap_words) { cudaFree(buf); return -need; }
-  std::vector<unsigned long long> h(n * per_launch);
-  CTB_CUDA(cudaMemcpy(h.data(), buf, h.size() * 8, cudaMemcpyDeviceToHost));
-  cudaFree(buf);
-  for (long i = 0; i < n; i++) {
-    unsigned long long* o = out + i * (2 + per_launch);
-    o[0] = (unsigned long long)trace_kind_[i]; o[1] = (unsigned long long)sm_count_;
-    memcpy(o + 2, h.data() + i * per_launch, per_launch * 8);
-  }
-  return n;
-}
-
-// The step's mat-vec launches alone (same kernels, same parameters, same order, no attention / embedding / argmax), replayed
-// as a CUDA graph: their summed duration under in-graph launch conditions is what bench.py's roofline for k_matvec uses.
+// The step's mat-vec phases alone (same kernel, same parameters, same order; no attention / embedding / pick), replayed as a
+// CUDA graph: their duration under in-step conditions is what bench.py's roofline for the mat-vec uses.  mask: bit k set =
+// keep the mat-vecs of kind k (0 = all).  with_attn: keep the attention phases too (times the dependency chain as it is).
 double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
-  matvec_mask_ = mask ? mask : ~0u;
+  if (!mask) mask = ~0u;
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   CTB_CUDA(cudaSetDevice(device_));
+  std::vector<StepOp> sel;
+  for (int i = 0; i <= n_body_; i++)
+    if (ops_[i].ph.kind == PH_MATVEC && ((mask >> ops_[i].mvk) & 1)) sel.push_back(ops_[i]);
+  if (sel.empty()) { if (launches) *launches = 0; return 0.0; }
+  upload_prog(d_prog_mv_, sel);
   cudaStream_t user = stream_, cap;
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   const long keep = launches_per_step_;
   cudaGraphExec_t ex = nullptr;
-  stream_ = cap; matvec_only_ = true;
+  stream_ = cap;
   try {
     cudaGraph_t g;
     CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_step(true, false);
+    enqueue_ops(sel, d_prog_mv_, (int)sel.size());
     CTB_CUDA(cudaStreamEndCapture(cap, &g));
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
     cudaGraphDestroy(g);
-  } catch (...) { stream_ = user; matvec_only_ = false; launches_per_step_ = keep; cudaStreamDestroy(cap); throw; }
-  if (launches) *launches = matvec_launches_;
-  stream_ = user; matvec_only_ = false; launches_per_step_ = keep;
+  } catch (...) { stream_ = user; launches_per_step_ = keep; cudaStreamDestroy(cap); throw; }
+  if (launches) *launches = (long)sel.size();
+  stream_ = user; launches_per_step_ = keep;
   cudaStreamDestroy(cap);
   cudaEvent_t e0, e1;
   CTB_CUDA(cudaEventCreate(&e0)); CTB_CUDA(cudaEventCreate(&e1));
@@ -564,10 +637,12 @@ void Engine::build_graphs() {
   cudaStream_t cap;
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   stream_ = cap;
+  ops_.back().ph.pk.out_tokens = d_tokens_out_;
+  upload_prog(d_prog_, ops_);
   auto capture = [&](bool logits, bool greedy) {
     cudaGraph_t g;
     CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_step(logits, greedy);
+    enqueue_ops(ops_, d_prog_, n_body_ + (logits ? 1 : 0) + (greedy ? 1 : 0));
     CTB_CUDA(cudaStreamEndCapture(cap, &g));
     cudaGraphExec_t ex;
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));

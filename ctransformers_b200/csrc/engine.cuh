@@ -3,9 +3,10 @@
 // llama_eval_internal (llama.cpp:2835-2981): last token's logits and post-final-norm hidden state end
 // up in host memory owned by the LLM object.
 //
-// B200 design: weights repacked once into coalesced planes (device_types.cuh); KV cache fp16;
-// one CUDA graph per decode step shape with {token, n_past} as device scalars, so the same graph
-// replays for every position; no per-eval graph build, no allocator, no thread pool.
+// B200 design: weights repacked once into the stream layout / coalesced planes (device_types.cuh); KV cache fp16;
+// a static op list per token whose K-quant mat-vecs, attention, embedding row and greedy pick run as the phases of
+// ONE persistent kernel (stream.cuh), replayed as a CUDA graph with {token, n_past} as device scalars; no per-eval
+// graph build, no allocator, no thread pool.
 #pragma once
 #include <cmath>
 #include <memory>
@@ -33,6 +34,10 @@ struct LayerW {
   const float* ffn_norm = nullptr;
 };
 
+struct Phase;    // stream.cuh: one phase of the persistent step kernel
+struct StepOp;   // engine.cu: one op of the per-token schedule
+struct MVParams;
+
 struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; long spec_hits = 0; };
 
 class Engine {
@@ -50,7 +55,6 @@ class Engine {
   // One eager (un-graphed) decode step at n_past with a CUDA event after every kernel; accumulates the
   // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
   double time_matvec_only(int reps, long* launches, unsigned mask = 0);
-  long trace_step(int token, int n_past, unsigned long long* out, long cap_words);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
 
   float* logits() { return h_logits_; }
@@ -100,24 +104,28 @@ class Engine {
   int sm_count_ = 148;
   long launches_per_step_ = 0;
 
-  DevMat upload_matrix(const GGUFTensor& t, uint8_t* staging);
-  const float* upload_vector(const GGUFFile& g, const std::string& name, bool required);
-  void enqueue_step(bool with_logits, bool greedy);
+  void init(const GGUFFile& g);
+  void release();
+  DevMat upload_matrix(const GGUFTensor& t, uint8_t* staging, int want_K, int want_M);
+  const float* upload_vector(const GGUFFile& g, const std::string& name, bool required, int want_n);
+  // the per-token schedule
+  std::vector<StepOp> ops_;      // EMBED, layers..., HEAD, PICK
+  int n_body_ = 0;               // ops before the HEAD mat-vec
+  Phase* d_prog_ = nullptr;      // device copy of ops_' phases (index = op index)
+  Phase* d_prog_mv_ = nullptr;   // scratch program of time_matvec_only
+  unsigned* d_sync_ = nullptr;   // grid-barrier words of the step kernel
+  int step_grid_ = 0, step_slots_ = 0;   // launch shape of the step kernel: CTAs, ring slots,
+  size_t step_smem_ = 0;                 // dynamic shared memory
+  bool fused_ = true;            // CTB_STEP_FUSE=0: one kernel per op
+  void build_ops();
+  void push_matvec(struct MVParams& p, int kind);
+  void upload_prog(Phase* dst, const std::vector<StepOp>& ops);
+  void enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n);
   void build_graphs();
   void destroy_graphs();
   enum : int { MVK_QKV = 0, MVK_WO = 1, MVK_UP = 2, MVK_DOWN = 3, MVK_OUT = 4 };   // which projection a mat-vec launch is
-  void launch_matvec(struct MVParams& p, int kind);
-  void launch_attn(const struct AttnParams& ap);
   bool profiling_ = false;
-  unsigned long long* trace_buf_ = nullptr;   // trace_step: device stamps, one slice per k_matvec launch
-  long trace_launch_ = 0;
-  std::vector<int> trace_kind_;
-  bool matvec_only_ = false;
-  unsigned matvec_mask_ = ~0u;  // time_matvec_only: bit k set = launches of kind k are kept
-  long matvec_launches_ = 0;   // k_matvec launches of the step being enqueued
-  bool fuse_attn_ = false;     // attention as the tail of the QKV launch: bit-exact but measured slower (430 vs 485 tokens/s); CTB_FUSED_ATTN=1 turns it on
-  int* attn_cnt_ = nullptr;    // [n_layer] finished row tiles of each layer's QKV launch
-  bool pdl_ = true;            // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
+  bool pdl_ = true;              // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)
   std::vector<cudaEvent_t> prof_ev_;
   std::vector<int> prof_kind_;
   void mark(int kind);

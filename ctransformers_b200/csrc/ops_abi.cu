@@ -1,5 +1,5 @@
 // Op-level C entry points (include/ctransformers_b200.h, part 2): each mirrors one ggml operator of the hot
-// path with plain host pointers, runs the SAME device code the engine runs (matvec.cuh / attention.cuh), and
+// path with plain host pointers, runs the SAME device code the engine runs (stream.cuh / matvec.cuh / attention.cuh), and
 // copies the result back.  Used by the parity tests and usable by a maintainer who wants to swap one op.
 #include <cmath>
 #include <cstdio>
@@ -13,6 +13,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "repack.cuh"
+#include "stream.cuh"
 #include "tables.hpp"
 
 using namespace ctb;
@@ -78,6 +79,16 @@ void upload(OwnedMat& o, int type, const void* blocks, int K, int M) {
   DevBuf raw(bytes);
   OPS_CUDA(cudaMemcpy(raw.p, blocks, bytes, cudaMemcpyHostToDevice));
   o.m.type = type; o.m.K = K; o.m.M = M; o.m.nb = K / block_elems(type); o.m.bytes = bytes;
+  if (type_is_kquant(type)) {   // the stream layout of the step kernel
+    const size_t sb = st_matrix_bytes(type, M, o.m.nb);
+    uint16_t* st = nullptr;
+    OPS_CUDA(cudaMalloc((void**)&st, sb));
+    o.bufs.push_back(st);
+    k_repack_stream<<<(int)std::min<size_t>((sb / 2 + 255) / 256, 4096), 256>>>(type, raw.as<uint8_t>(), M, o.m.nb, st);
+    OPS_CUDA(cudaDeviceSynchronize());
+    o.m.st = (const uint8_t*)st;
+    return;
+  }
   const PlaneSizes ps = plane_sizes(type, M, o.m.nb, bytes);
   uint16_t* pl[4] = {nullptr, nullptr, nullptr, nullptr};
   const size_t sz[4] = {ps.qs, ps.qh, ps.sc, ps.d};
@@ -88,17 +99,39 @@ void upload(OwnedMat& o, int type, const void* blocks, int K, int M) {
   o.m.qs = (const uint8_t*)pl[0]; o.m.qh = (const uint8_t*)pl[1]; o.m.sc = (const uint8_t*)pl[2]; o.m.d = pl[3];
 }
 
+int sm_count() {
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
+  return n_sm;
+}
+
+// a program of phases through the persistent step kernel, exactly as the engine launches it
+void run_phases(const std::vector<Phase>& phs) {
+  static unsigned* d_sync = nullptr;
+  if (!d_sync) { OPS_CUDA(cudaMalloc((void**)&d_sync, 64)); OPS_CUDA(cudaMemset(d_sync, 0, 64)); }
+  const StepLaunch L = step_launch_shape(phs.data(), (int)phs.size(), sm_count(), step_max_dyn_smem());
+  if (L.n_slots < 2) throw std::runtime_error("rows too long for the step kernel's shared memory");
+  OPS_CUDA(step_set_smem_limit(L.smem));
+  DevBuf dprog((phs.size() + 1) * sizeof(Phase));
+  OPS_CUDA(cudaMemcpy(dprog.p, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+  OPS_CUDA(launch_step(L, 0, dprog.as<Phase>(), (int)phs.size(), d_sync));
+  OPS_CUDA(cudaGetLastError());
+  OPS_CUDA(cudaDeviceSynchronize());
+}
+
 void run_matvec(MVParams& p) {
   p.silu_tab = tables().silu;
   p.gelu_tab = tables().gelu;
+  if (step_supports(p)) {
+    run_phases({matvec_phase(p)});
+    return;
+  }
   static bool attr = false;
   if (!attr) {
     OPS_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
     attr = true;
   }
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, 0);
-  const MVLaunch L = matvec_launch_shape(p, n_sm);
+  const MVLaunch L = matvec_launch_shape(p, sm_count());
   OPS_CUDA(launch_matvec_kernel(L, 0, p));
   OPS_CUDA(cudaGetLastError());
 }
@@ -112,7 +145,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_stage_dump(const float* x, const
   q.x = x;
   NormPre np;
   preload_norm(np, nw, nb, mode, K);
-  stage_activation(q, np, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
+  stage_activation<MV_THREADS, 0>(q, np, nw, nb, norm_out, mode, eps, K, act, smem, red, true);
   const size_t n = act_smem_bytes(act, K);
   for (size_t i = threadIdx.x; i < n; i += MV_THREADS) dump[i] = smem[i];
 }
@@ -125,7 +158,7 @@ __global__ void __launch_bounds__(MV_THREADS) k_gate_dump(const float* gate, con
   q.x = gate; q.x2 = up; q.x_mode = 1; q.silu_tab = silu_tab;
   NormPre np;
   preload_norm(np, nullptr, nullptr, NORM_NONE, M);
-  stage_activation(q, np, nullptr, nullptr, nullptr, NORM_NONE, 0.f, M, ACT_F32, smem, red, false);
+  stage_activation<MV_THREADS, 0>(q, np, nullptr, nullptr, nullptr, NORM_NONE, 0.f, M, ACT_F32, smem, red, false);
   const float* f = (const float*)smem;
   for (int i = threadIdx.x; i < M; i += MV_THREADS) out[i] = f[i];
 }
@@ -312,20 +345,30 @@ int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const f
   });
 }
 
-// Host-side view of how a K-quant launch is cut up (no GPU needed): the launch geometry and the first row tile of every CTA.
+// Host-side view of how a K-quant mat-vec phase is cut up (no GPU needed): the 16-row tile range of every CTA.
 int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int n_sm, int* first_tile, int* meta) {
-  if (nseg < 1 || nseg > MV_MAX_SEG || K <= 0 || K % 256 != 0) return -1;
+  if (nseg < 1 || nseg > MV_MAX_SEG || K <= 0 || K % 256 != 0 || n_sm < 1) return -1;
   MVParams p{};
   p.K = K; p.nseg = nseg; p.act = ACT_Q8_K;
   for (int s = 0; s < nseg; s++) {
     if (!type_is_kquant(types[s]) || rows[s] < 1) return -1;
     p.seg[s].w.type = types[s]; p.seg[s].w.K = K; p.seg[s].w.M = rows[s]; p.seg[s].w.nb = K / 256;
   }
-  const MVLaunch L = matvec_launch_shape(p, n_sm);
   TileSpace ts;
   ts.init(p);
-  for (int c = 0; c <= L.grid; c++) first_tile[c] = ts.boundary(c, L.grid);
-  meta[0] = L.grid; meta[1] = (int)L.smem; meta[2] = p.def_max; meta[3] = ts.ntiles; meta[4] = MV_WARPS; meta[5] = MV_KQ_ROWS; meta[6] = MV_SMEM_LIMIT;
+  const int nb = K / 256;
+  long max_items = 0;
+  for (int c = 0; c <= n_sm; c++) first_tile[c] = ts.boundary(c, n_sm);
+  for (int c = 0; c < n_sm; c++) {
+    long items = 0;
+    for (int tile = first_tile[c]; tile < first_tile[c + 1]; tile++) {
+      int tl = tile;
+      const int kb = st_chunk_blocks(types[ts.locate(tl)]);
+      items += (nb + kb - 1) / kb;
+    }
+    max_items = std::max(max_items, items);
+  }
+  meta[0] = n_sm; meta[1] = ST_SLOT; meta[2] = ST_MAXT; meta[3] = ts.ntiles; meta[4] = ST_W; meta[5] = ST_ROWS; meta[6] = (int)max_items;
   return 0;
 }
 

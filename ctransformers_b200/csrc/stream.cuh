@@ -1,0 +1,756 @@
+// The persistent decode-step kernel (sm_100a): every K-quant mat-vec of a token, plus attention, embedding row and greedy
+// pick, as PHASES of one launch — one CTA per SM, device-side grid barriers instead of kernel boundaries, and a weight
+// stream that never stops at them.
+//
+// Replaces, bit-exactly, what ggml_graph_compute does per token for a Llama / Falcon graph (llama.cpp:2162-2798, 2835-2981):
+//   ggml_compute_forward_mul_mat over Q4_K / Q5_K / Q6_K weights with Q8_K activations   ggml.c:11031-11245
+//   ggml_vec_dot_q4_K_q8_K / q5_K / q6_K, AVX2 variants                                  k_quants.c:2651-2714, 3174-3262, 3794-3872
+//   norm + quantize prologue and residual / SiLU / GELU epilogue                         matvec.cuh (shared with k_matvec)
+//   RoPE, KV store, K·q, softmax, V·p                                                    attention.cuh attn_body
+//
+// Structure of a CTA (ST_W consumer warps + 1 producer warp):
+//   producer warp   walks the phase list ahead of everybody else and keeps a ring of ST_SLOT-byte shared-memory slots full:
+//                   one cp.async.bulk (TMA bulk copy, completion on an mbarrier) per work item.  Weights do not depend on
+//                   activations, so the copies for the next phases are already in flight (or landed) while the consumers
+//                   still wait at a grid barrier, stage an activation vector or run attention: HBM never idles.
+//   work item       (16-row tile, chunk of 3-4 consecutive 256-weight blocks): 16 x {144,176,210} bytes per block, contiguous
+//                   in the STREAM layout written at load time (k_repack_stream).  Items are numbered in one sequence that both
+//                   sides enumerate identically; item n lives in slot n % S and belongs to consumer warp n % ST_W.
+//   consumer warp   per block: the 8 (sub-block) x 8 (AVX lane) 4-element integer dots of 16 rows come from 8 tensor-core
+//                   instructions — mma.sync.m16n8k32 u8 x s8 with A = 16 rows x one 32-weight sub-block (nibbles unpacked in
+//                   registers) and B = that sub-block's int8 activations laid out BLOCK-DIAGONALLY (column l holds elements
+//                   4l..4l+3, zero elsewhere), so D[row][l] is exactly what int32 lane l of the reference's AVX2 kernel holds
+//                   after maddubs/madd.  Scales are folded with dp2a, the per-block fp32 terms (exact integers) are parked in
+//                   registers, and the reference's fmadd chain per AVX lane is replayed IN BLOCK ORDER: a chunk that is not
+//                   the first of its tile receives the running fp32 state of the 16 rows from the warp that folded the
+//                   previous chunk (shared-memory mailbox + flag), folds its blocks and passes the state on; the last chunk
+//                   ends with hsum_float_8's tree and the epilogue.  Any partition of a row therefore gives the same bits.
+//   grid barrier    one atomic arrive + acquire spin per phase boundary (all phases depend on the whole previous output).
+//
+// Algorithmic HBM bytes: the GGUF bytes of the weights, once per token (same byte count in the stream layout).
+#pragma once
+#include "matvec.cuh"
+
+namespace ctb {
+
+#ifndef CTB_ST_WARPS
+#define CTB_ST_WARPS 11
+#endif
+constexpr int ST_W = CTB_ST_WARPS;      // consumer warps
+constexpr int ST_NT = ST_W * 32;        // consumer threads (threads 0 .. ST_NT-1)
+constexpr int ST_THREADS = ST_NT + 32;  // + the producer warp
+constexpr int ST_SLOT = 10240;          // ring slot: holds 4 Q4_K / 3 Q5_K / 3 Q6_K blocks of a 16-row tile
+constexpr int ST_MAX_SLOTS = 20;
+constexpr int ST_MAXT = 16;             // tiles of a CTA whose fold chains are alive at the same time (one mailbox each)
+constexpr int ST_ROWS = 16;
+constexpr int ST_BAR = 1;               // named barrier of the consumer warps
+constexpr int ST_STATE = 6;             // floats of fold state per thread: 4 AVX-lane accumulators + up to 2 mins accumulators
+
+__host__ __device__ inline int st_row_block_bytes(int type) { return type == GT_Q4_K ? 144 : (type == GT_Q5_K ? 176 : 210); }
+__host__ __device__ inline int st_block_bytes(int type) { return ST_ROWS * st_row_block_bytes(type); }   // 2304 / 2816 / 3360
+__host__ __device__ inline int st_chunk_blocks(int type) { return type == GT_Q4_K ? 4 : 3; }
+__host__ __device__ inline int st_tile_cost(int type) { return type == GT_Q6_K ? 105 : (type == GT_Q5_K ? 88 : 72); }   // bytes per row-block / 2
+__host__ __device__ inline size_t st_matrix_bytes(int type, int M, int nb) { return (size_t)((M + ST_ROWS - 1) / ST_ROWS) * nb * st_block_bytes(type); }
+
+// ---------------------------------------------------------------------------------------------
+// STREAM layout.  Tile i = rows 16i..16i+15; piece (i, b) = block b of those rows at byte ((i * nb + b) * st_block_bytes).
+// Inside a piece, for mma thread (g = lane >> 2, t = lane & 3), h in {0,1} (AVX lane l = t + 4h), rr in {0,1} (row g + 8rr):
+//   Q4_K  [0,2048)    16 B at ((h*2+rr)*32 + lane)*16: words j = 0..3 (32-weight pairs) of AVX lane l of that row  (k_quants.h:76-82)
+//         [2048,2304) 16 B at (rr*8+g)*16: d, dmin, scales[12]
+//   Q5_K  [0,2048)    as Q4_K;  [2048,2560) 4 B at ((h*2+rr)*32 + lane)*4: qh word l;  [2560,2816) headers      (k_quants.h:98-104)
+//   Q6_K  [0,2048)    16 B: ql words (half 0, v 0) (0,1) (1,0) (1,1) of AVX lane l;  [2048,3072) 8 B at ((h*2+rr)*32 + lane)*8: qh
+//         words of halves 0, 1;  [3072,3328) 16 int8 scales per row;  [3328,3360) fp16 d per row                (k_quants.h:112-117)
+// A warp-wide 16-byte load of one (h, rr) plane touches 512 consecutive bytes: conflict-free.  Rows >= M are zero blocks.
+__device__ __forceinline__ void st_decode(int type, int o, int& rl, int& src) {
+  const int q4 = (type == GT_Q6_K) ? 0 : (type == GT_Q5_K ? 48 : 16);   // raw offset of the 128 nibble bytes
+  if (o < 2048) {
+    const int q = o >> 4, hr = q >> 5, lane = q & 31, h = hr >> 1, rr = hr & 1, g = lane >> 2, t = lane & 3, l = t + 4 * h;
+    const int wi = (o >> 2) & 3, byte = o & 3;
+    rl = rr * 8 + g;
+    src = type == GT_Q6_K ? ((wi >> 1) * 64 + (wi & 1) * 32 + 4 * l + byte) : (q4 + 32 * wi + 4 * l + byte);
+    return;
+  }
+  if (type == GT_Q4_K) { const int r = o - 2048; rl = r >> 4; src = r & 15; return; }
+  if (type == GT_Q5_K) {
+    if (o < 2560) {
+      const int q = (o - 2048) >> 2, hr = q >> 5, lane = q & 31, h = hr >> 1, rr = hr & 1, g = lane >> 2, t = lane & 3;
+      rl = rr * 8 + g; src = 16 + 4 * (t + 4 * h) + (o & 3);
+      return;
+    }
+    const int r = o - 2560; rl = r >> 4; src = r & 15; return;
+  }
+  if (o < 3072) {
+    const int r = o - 2048, q = r >> 3, hr = q >> 5, lane = q & 31, h = hr >> 1, rr = hr & 1, g = lane >> 2, t = lane & 3;
+    rl = rr * 8 + g; src = 128 + ((r >> 2) & 1) * 32 + 4 * (t + 4 * h) + (r & 3);
+    return;
+  }
+  if (o < 3328) { const int r = o - 3072; rl = r >> 4; src = 192 + (r & 15); return; }
+  rl = (o - 3328) >> 1; src = 208;
+}
+
+// GGUF array-of-blocks → stream layout, 2 bytes per thread-iteration
+static __global__ void k_repack_stream(int type, const uint8_t* __restrict__ raw, int M, int nb, uint16_t* __restrict__ st) {
+  const int rbb = st_row_block_bytes(type), half = rbb * ST_ROWS / 2;
+  const size_t n_units = (size_t)((M + ST_ROWS - 1) / ST_ROWS) * nb * half;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_units; idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t piece = idx / half;
+    const int o = (int)(idx % half) * 2;
+    const size_t tile = piece / nb;
+    const int b = (int)(piece % nb);
+    int rl, src;
+    st_decode(type, o, rl, src);
+    const size_t row = tile * ST_ROWS + rl;
+    st[idx] = row < (size_t)M ? *(const uint16_t*)(raw + (row * nb + b) * rbb + src) : (uint16_t)0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX: mbarrier, bulk copy, tensor-core mma
+__device__ __forceinline__ uint32_t st_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem(bar)) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(st_smem(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { } }
+// global → shared bulk copy (TMA, SASS UBLKCP), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(dst)), "l"(src), "r"(bytes), "r"(st_smem(bar)) : "memory");
+}
+// D(16x8, s32) = A(16x32, u8, row) · B(32x8, s8, col) + C.  Fragments (PTX ISA, m16n8k32 8-bit): a0 = row g, k 4t..4t+3; a1 = row
+// g+8, same k; a2 = row g, k 16+4t..; a3 = row g+8, k 16+4t..;  b0 = k 4t..4t+3, col g;  b1 = k 16+4t.., col g;  d0/d1 = row g,
+// cols 2t, 2t+1;  d2/d3 = row g+8, cols 2t, 2t+1.
+__device__ __forceinline__ void mma_u8s8(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, int c0, int c1) {
+  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c0), "r"(c1), "r"(c0), "r"(c1));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Activation vector in shared memory: the Q8_K image written by stage_activation (qs lane-major per block, d, bsums) plus
+//   pairs  per block 4 words: (bsums[4k]+bsums[4k+1]) | (bsums[4k+2]+bsums[4k+3]) << 16 — the operands of the Q4_K / Q5_K mins terms
+//   cneg   Q6_K phases: per block [t][group][c] int32 = -32 · Σ of the 4 activations of AVX lane l = 2t+c of 32-weight group
+//          `group`: the accumulator input that turns u·q8 into (u-32)·q8 (the AVX2 kernel subtracts maddubs(32, q8), k_quants.c:3829-3843)
+struct StAct {
+  const int8_t* qs;
+  const float* d;
+  const uint32_t* pairs;
+  const int* cneg;
+};
+__host__ __device__ inline size_t st_off_pairs(int K) { return ((((size_t)K + 15) & ~(size_t)15) + q8k_d_bytes(K) + (size_t)(K / 16) * 2 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t st_act_bytes(int K, bool q6) { return st_off_pairs(K) + (size_t)(K / 256) * 16 + (q6 ? (size_t)K : 0) + 16; }
+
+template <int NT, int BAR>
+__device__ __forceinline__ StAct st_act_extras(uint8_t* smem, int K, bool q6) {
+  const ActView a = act_view(ACT_Q8_K, K, smem);
+  StAct s;
+  s.qs = a.qs; s.d = a.d;
+  uint32_t* pairs = (uint32_t*)(smem + st_off_pairs(K));
+  int* cneg = (int*)(smem + st_off_pairs(K) + (size_t)(K / 256) * 16);
+  s.pairs = pairs; s.cneg = cneg;
+  const int nb = K >> 8;
+  for (int i = threadIdx.x; i < nb * 4; i += NT) {
+    const int16_t* b4 = a.bs + (i >> 2) * 16 + 4 * (i & 3);
+    const int p0 = (int)b4[0] + (int)b4[1], p1 = (int)b4[2] + (int)b4[3];
+    pairs[i] = (uint32_t)(p0 & 0xffff) | ((uint32_t)p1 << 16);
+  }
+  if (q6) {
+    for (int i = threadIdx.x; i < nb * 64; i += NT) {
+      const int b = i >> 6, grp = (i >> 3) & 7, l = i & 7;
+      const int w = *(const int*)(a.qs + q8k_word_offset(b, grp, l));
+      cneg[((b * 4 + (l >> 1)) * 8 + grp) * 2 + (l & 1)] = -32 * __dp4a(0x01010101, w, 0);
+    }
+  }
+  bar_sync<BAR, NT>();
+  return s;
+}
+
+// unpack the 12 scale bytes of a Q4_K/Q5_K header (k_quants.c:306-313 get_scale_min_k4, all 8 at once)
+__device__ __forceinline__ void unpack_k4(uint32_t s0, uint32_t s1, uint32_t s2, uint32_t& sc03, uint32_t& sc47, uint32_t& m03, uint32_t& m47) {
+  sc03 = s0 & 0x3f3f3f3fu;
+  m03 = s1 & 0x3f3f3f3fu;
+  sc47 = (s2 & 0x0f0f0f0fu) | (((s0 >> 6) & 0x03030303u) << 4);
+  m47 = ((s2 >> 4) & 0x0f0f0f0fu) | (((s1 >> 6) & 0x03030303u) << 4);
+}
+__device__ __forceinline__ int pack16(int lo, int hi) { return (int)__byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+// Σ_s scale_s · dot_s over the 8 sub-block dots of one (row, AVX lane); every dot fits int16, the scales are bytes
+__device__ __forceinline__ int scale_fold8(int d0, int d1, int d2, int d3, int d4, int d5, int d6, int d7, uint32_t s03, uint32_t s47) {
+  int s = __dp2a_lo(pack16(d0, d1), (int)s03, 0);
+  s = __dp2a_hi(pack16(d2, d3), (int)s03, s);
+  s = __dp2a_lo(pack16(d4, d5), (int)s47, s);
+  s = __dp2a_hi(pack16(d6, d7), (int)s47, s);
+  return s;
+}
+
+// What one block contributes to this thread's share of the 16 rows: p[rr*2+c] = (float) of int32 lane l = 2t+c of row g+8rr;
+// dd[rr] = y.d·d; mins: Q4_K pm[rr] = mins lane k = t of row g+8rr (ddm[rr] = -y.d·dmin); Q5_K pm[0] = the scalar mins term of
+// row g+8(t&1) (ddm[0]); Q6_K none.
+struct Terms { float p[4]; float pm[2]; float dd[2]; float ddm[2]; };
+
+__device__ __forceinline__ void load_b_operands(const StAct& a, int b, int g, int t, uint32_t (&bA)[8], uint32_t (&bB)[8]) {
+  // block-diagonal B: thread (g, t) holds rows 4t..4t+3 / 16+4t.. of column g, which are non-zero only for g == t / g == t+4
+#pragma unroll
+  for (int s = 0; s < 8; s++) { bA[s] = 0u; bB[s] = 0u; }
+  if (g == t) {
+    const int4 lo = *(const int4*)(a.qs + b * 256 + t * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + t * 16);
+    bA[0] = lo.x; bA[1] = lo.y; bA[2] = lo.z; bA[3] = lo.w; bA[4] = hi.x; bA[5] = hi.y; bA[6] = hi.z; bA[7] = hi.w;
+  }
+  if (g == t + 4) {
+    const int4 lo = *(const int4*)(a.qs + b * 256 + g * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + g * 16);
+    bB[0] = lo.x; bB[1] = lo.y; bB[2] = lo.z; bB[3] = lo.w; bB[4] = hi.x; bB[5] = hi.y; bB[6] = hi.z; bB[7] = hi.w;
+  }
+}
+
+template <int TYPE>
+__device__ __forceinline__ void block_terms(const uint8_t* blk, int b, const StAct& a, int lane, Terms& r);
+
+// k_quants.c:2651-2714
+template <>
+__device__ __forceinline__ void block_terms<GT_Q4_K>(const uint8_t* blk, int b, const StAct& a, int lane, Terms& r) {
+  const int g = lane >> 2, t = lane & 3;
+  const int4* qp = (const int4*)blk;
+  const int4 w00 = qp[lane], w01 = qp[32 + lane], w10 = qp[64 + lane], w11 = qp[96 + lane];
+  const int4 h0 = ((const int4*)(blk + 2048))[g], h1 = ((const int4*)(blk + 2048))[8 + g];
+  uint32_t bA[8], bB[8];
+  load_b_operands(a, b, g, t, bA, bB);
+  const uint32_t W[4][4] = {{(uint32_t)w00.x, (uint32_t)w01.x, (uint32_t)w10.x, (uint32_t)w11.x}, {(uint32_t)w00.y, (uint32_t)w01.y, (uint32_t)w10.y, (uint32_t)w11.y},
+                            {(uint32_t)w00.z, (uint32_t)w01.z, (uint32_t)w10.z, (uint32_t)w11.z}, {(uint32_t)w00.w, (uint32_t)w01.w, (uint32_t)w10.w, (uint32_t)w11.w}};
+  int D[8][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    mma_u8s8(D[2 * j], W[j][0] & 0x0f0f0f0fu, W[j][1] & 0x0f0f0f0fu, W[j][2] & 0x0f0f0f0fu, W[j][3] & 0x0f0f0f0fu, bA[2 * j], bB[2 * j], 0, 0);
+    mma_u8s8(D[2 * j + 1], (W[j][0] >> 4) & 0x0f0f0f0fu, (W[j][1] >> 4) & 0x0f0f0f0fu, (W[j][2] >> 4) & 0x0f0f0f0fu, (W[j][3] >> 4) & 0x0f0f0f0fu, bA[2 * j + 1],
+             bB[2 * j + 1], 0, 0);
+  }
+  const float yd = a.d[b];
+  const uint32_t pw = a.pairs[b * 4 + t];
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    const int4 h = rr ? h1 : h0;
+    uint32_t sc03, sc47, m03, m47;
+    unpack_k4((uint32_t)h.y, (uint32_t)h.z, (uint32_t)h.w, sc03, sc47, m03, m47);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const int i = rr * 2 + c;
+      r.p[i] = (float)scale_fold8(D[0][i], D[1][i], D[2][i], D[3][i], D[4][i], D[5][i], D[6][i], D[7][i], sc03, sc47);
+    }
+    r.dd[rr] = __fmul_rn(yd, h2f((uint16_t)((uint32_t)h.x & 0xffffu)));
+    r.ddm[rr] = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)h.x >> 16)));
+    // mins lane k = t: m[2k]·(bsums[4k]+bsums[4k+1]) + m[2k+1]·(bsums[4k+2]+bsums[4k+3])
+    const uint32_t mw = (t < 2 ? m03 : m47) >> ((t & 1) * 16);
+    r.pm[rr] = (float)__dp2a_lo((int)pw, (int)mw, 0);
+  }
+}
+
+// k_quants.c:3174-3262
+template <>
+__device__ __forceinline__ void block_terms<GT_Q5_K>(const uint8_t* blk, int b, const StAct& a, int lane, Terms& r) {
+  const int g = lane >> 2, t = lane & 3;
+  const int4* qp = (const int4*)blk;
+  const int4 w00 = qp[lane], w01 = qp[32 + lane], w10 = qp[64 + lane], w11 = qp[96 + lane];
+  const uint32_t* hp = (const uint32_t*)(blk + 2048);
+  const uint32_t HB[4] = {hp[lane], hp[32 + lane], hp[64 + lane], hp[96 + lane]};
+  const int4 h0 = ((const int4*)(blk + 2560))[g], h1 = ((const int4*)(blk + 2560))[8 + g];
+  uint32_t bA[8], bB[8];
+  load_b_operands(a, b, g, t, bA, bB);
+  const uint32_t W[4][4] = {{(uint32_t)w00.x, (uint32_t)w01.x, (uint32_t)w10.x, (uint32_t)w11.x}, {(uint32_t)w00.y, (uint32_t)w01.y, (uint32_t)w10.y, (uint32_t)w11.y},
+                            {(uint32_t)w00.z, (uint32_t)w01.z, (uint32_t)w10.z, (uint32_t)w11.z}, {(uint32_t)w00.w, (uint32_t)w01.w, (uint32_t)w10.w, (uint32_t)w11.w}};
+  int D[8][4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {   // bit s of a qh byte: 5th bit of the element in sub-block s
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      lo[i] = (W[j][i] & 0x0f0f0f0fu) | (((HB[i] >> (2 * j)) & 0x01010101u) << 4);
+      hi[i] = ((W[j][i] >> 4) & 0x0f0f0f0fu) | (((HB[i] >> (2 * j + 1)) & 0x01010101u) << 4);
+    }
+    mma_u8s8(D[2 * j], lo[0], lo[1], lo[2], lo[3], bA[2 * j], bB[2 * j], 0, 0);
+    mma_u8s8(D[2 * j + 1], hi[0], hi[1], hi[2], hi[3], bA[2 * j + 1], bB[2 * j + 1], 0, 0);
+  }
+  const float yd = a.d[b];
+  const uint4 pw = *(const uint4*)(a.pairs + b * 4);
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    const int4 h = rr ? h1 : h0;
+    uint32_t sc03, sc47, m03, m47;
+    unpack_k4((uint32_t)h.y, (uint32_t)h.z, (uint32_t)h.w, sc03, sc47, m03, m47);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const int i = rr * 2 + c;
+      r.p[i] = (float)scale_fold8(D[0][i], D[1][i], D[2][i], D[3][i], D[4][i], D[5][i], D[6][i], D[7][i], sc03, sc47);
+    }
+    r.dd[rr] = __fmul_rn(yd, h2f((uint16_t)((uint32_t)h.x & 0xffffu)));
+    if (rr == (t & 1)) {   // the scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]), kept by thread t = rr of the row's quad
+      int hs = __dp2a_lo((int)pw.x, (int)m03, 0);
+      hs = __dp2a_hi((int)pw.y, (int)m03, hs);
+      hs = __dp2a_lo((int)pw.z, (int)m47, hs);
+      hs = __dp2a_hi((int)pw.w, (int)m47, hs);
+      r.pm[0] = (float)hs;
+      r.ddm[0] = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)h.x >> 16)));
+    }
+  }
+}
+
+// k_quants.c:3794-3872
+template <>
+__device__ __forceinline__ void block_terms<GT_Q6_K>(const uint8_t* blk, int b, const StAct& a, int lane, Terms& r) {
+  const int g = lane >> 2, t = lane & 3;
+  const int4* qp = (const int4*)blk;
+  const int2* hp = (const int2*)(blk + 2048);
+  const int4 QL[4] = {qp[lane], qp[32 + lane], qp[64 + lane], qp[96 + lane]};   // index h*2+rr; words (half 0: A, B) (half 1: A, B)
+  const int2 QH[4] = {hp[lane], hp[32 + lane], hp[64 + lane], hp[96 + lane]};
+  const int4 s0 = ((const int4*)(blk + 3072))[g], s1 = ((const int4*)(blk + 3072))[8 + g];
+  const uint16_t d0 = ((const uint16_t*)(blk + 3328))[g], d1 = ((const uint16_t*)(blk + 3328))[8 + g];
+  uint32_t bA[8], bB[8];
+  load_b_operands(a, b, g, t, bA, bB);
+  const int4* cp = (const int4*)(a.cneg + (b * 4 + t) * 16);   // [group][c] for this thread's two columns
+  const int4 cn[4] = {cp[0], cp[1], cp[2], cp[3]};
+  const int C[8][2] = {{cn[0].x, cn[0].y}, {cn[0].z, cn[0].w}, {cn[1].x, cn[1].y}, {cn[1].z, cn[1].w}, {cn[2].x, cn[2].y}, {cn[2].z, cn[2].w}, {cn[3].x, cn[3].y}, {cn[3].z, cn[3].w}};
+  int D[8][4];
+#pragma unroll
+  for (int jj = 0; jj < 2; jj++) {
+    uint32_t u[4][4];   // [m][fragment register]
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      // fragment register order a0..a3 = (h0,rr0) (h0,rr1) (h1,rr0) (h1,rr1) = plane index i
+      const uint32_t A = (uint32_t)(jj ? QL[i].z : QL[i].x), B = (uint32_t)(jj ? QL[i].w : QL[i].y), H = (uint32_t)(jj ? QH[i].y : QH[i].x);
+      u[0][i] = (A & 0x0f0f0f0fu) | ((H << 4) & 0x30303030u);
+      u[1][i] = (B & 0x0f0f0f0fu) | ((H << 2) & 0x30303030u);
+      u[2][i] = ((A >> 4) & 0x0f0f0f0fu) | (H & 0x30303030u);
+      u[3][i] = ((B >> 4) & 0x0f0f0f0fu) | ((H >> 2) & 0x30303030u);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+      const int grp = jj * 4 + m;
+      mma_u8s8(D[grp], u[m][0], u[m][1], u[m][2], u[m][3], bA[grp], bB[grp], C[grp][0], C[grp][1]);
+    }
+  }
+  const float yd = a.d[b];
+  const int par = t >> 1;   // this thread's columns 2t, 2t+1 are AVX lanes of the first (par 0) or second (par 1) 16 weights of each group
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    const int4 sv = rr ? s1 : s0;
+    // int8 scale of (half jj, group m, par): byte 2(m&1)+par of word jj*2+(m>>1) -> S[jj] = scales of m = 0..3 as 4 signed bytes
+    const uint32_t sel = par ? 0x7531u : 0x6420u;
+    const uint32_t S0 = __byte_perm((uint32_t)sv.x, (uint32_t)sv.y, sel), S1 = __byte_perm((uint32_t)sv.z, (uint32_t)sv.w, sel);
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      const int i = rr * 2 + c;
+      r.p[i] = (float)scale_fold8(D[0][i], D[1][i], D[2][i], D[3][i], D[4][i], D[5][i], D[6][i], D[7][i], S0, S1);
+    }
+    r.dd[rr] = __fmul_rn(yd, h2f(rr ? d1 : d0));
+  }
+}
+
+template <int TYPE> struct StTraits;
+template <> struct StTraits<GT_Q4_K> { static constexpr int KB = 4, BB = 2304, NM = 2; };
+template <> struct StTraits<GT_Q5_K> { static constexpr int KB = 3, BB = 2816, NM = 1; };
+template <> struct StTraits<GT_Q6_K> { static constexpr int KB = 3, BB = 3360, NM = 0; };
+
+// One work item: blocks [b0, b0 + nblk) of the 16-row tile whose pieces lie in `slot`.  Integer work first (the slot is
+// released as soon as the last weight word has been read), then the ordered fp32 fold: state in from the mailbox unless this
+// is the tile's first chunk, blocks folded in order, state out unless it is the last chunk — then hsum_float_8 and the epilogue.
+template <int TYPE>
+__device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_bar, int nblk, int b0, int kc, bool last, const StAct& a, int lane,
+                                         volatile float* mail, volatile int* flag, const MVSeg& sg, const MVParams& p, int row0) {
+  constexpr int KB = StTraits<TYPE>::KB, BB = StTraits<TYPE>::BB, NM = StTraits<TYPE>::NM;
+  Terms tr[KB];
+#pragma unroll
+  for (int i = 0; i < KB; i++)
+    if (i < nblk) block_terms<TYPE>(slot + i * BB, b0 + i, a, lane, tr[i]);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty_bar);   // every lane has its weight words in registers: the producer may refill the slot
+
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accm[2] = {0.f, 0.f};
+  if (kc > 0) {
+    if (lane == 0) while (*flag < kc) { }
+    __syncwarp();
+    __threadfence_block();
+#pragma unroll
+    for (int i = 0; i < 4; i++) acc[i] = mail[i * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < NM; i++) accm[i] = mail[(4 + i) * 32 + lane];
+  }
+#pragma unroll
+  for (int i = 0; i < KB; i++) {
+    if (i < nblk) {
+      // one fmadd per block and AVX lane, blocks in order (k_quants.c:2706, 3253, 3864); mins: 2699-2701 (Q4_K), 3199-3201 (Q5_K)
+#pragma unroll
+      for (int q = 0; q < 4; q++) acc[q] = __fmaf_rn(tr[i].dd[q >> 1], tr[i].p[q], acc[q]);
+#pragma unroll
+      for (int q = 0; q < NM; q++) accm[q] = __fmaf_rn(tr[i].ddm[q], tr[i].pm[q], accm[q]);
+    }
+  }
+  if (!last) {
+    __syncwarp();   // all lanes have read the incoming state before anybody overwrites the mailbox
+#pragma unroll
+    for (int i = 0; i < 4; i++) mail[i * 32 + lane] = acc[i];
+#pragma unroll
+    for (int i = 0; i < NM; i++) mail[(4 + i) * 32 + lane] = accm[i];
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *flag = kc + 1;
+    return;
+  }
+  // hsum_float_8 (ggml.c:609-615): res[l] = x[l] + x[l+4]; (res[0]+res[2]) + (res[1]+res[3]).  Thread t holds x[2t], x[2t+1].
+  const int t = lane & 3, g = lane >> 2;
+  float out[2];
+#pragma unroll
+  for (int rr = 0; rr < 2; rr++) {
+    float u0 = acc[rr * 2], u1 = acc[rr * 2 + 1];
+    u0 = __fadd_rn(u0, __shfl_xor_sync(0xffffffffu, u0, 2));   // t = 0: x0+x4, t = 1: x2+x6
+    u1 = __fadd_rn(u1, __shfl_xor_sync(0xffffffffu, u1, 2));   // t = 0: x1+x5, t = 1: x3+x7
+    u0 = __fadd_rn(u0, __shfl_xor_sync(0xffffffffu, u0, 1));   // res[0]+res[2]
+    u1 = __fadd_rn(u1, __shfl_xor_sync(0xffffffffu, u1, 1));   // res[1]+res[3]
+    float v = __fadd_rn(u0, u1);
+    if (TYPE == GT_Q4_K) {          // acc_m: (m0+m2) + (m1+m3), then added to the total (k_quants.c:2709-2712)
+      float m = accm[rr];
+      m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = __fadd_rn(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      v = __fadd_rn(v, m);
+    } else if (TYPE == GT_Q5_K) {   // the scalar mins chain of row g+8rr lives in thread t = rr of the quad
+      v = __fadd_rn(v, __shfl_sync(0xffffffffu, accm[0], (lane & ~3) + rr));
+    }
+    out[rr] = v;
+  }
+  if (t < 2) {
+    const int row = row0 + g + 8 * t;
+    if (row < sg.w.M) store_epilogue(sg, p, row, t ? out[1] : out[0]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The 16-row tiles of a phase's matrices, concatenated; CTA c owns a contiguous, byte-balanced range of them.
+struct TileSpace {
+  int tiles[MV_MAX_SEG], cost[MV_MAX_SEG], nseg, ntiles;
+  long total;   // Σ tiles·cost
+  __host__ __device__ __forceinline__ void init(const MVParams& p) {
+    nseg = p.nseg; ntiles = 0; total = 0;
+#pragma unroll
+    for (int s = 0; s < MV_MAX_SEG; s++) {
+      tiles[s] = s < p.nseg ? (p.seg[s].w.M + ST_ROWS - 1) / ST_ROWS : 0;
+      cost[s] = s < p.nseg ? st_tile_cost(p.seg[s].w.type) : 1;
+      ntiles += tiles[s]; total += (long)tiles[s] * cost[s];
+    }
+  }
+  // matrix a tile of the concatenated space belongs to; `tile` becomes the tile index inside that matrix
+  __host__ __device__ __forceinline__ int locate(int& tile) const {
+    static_assert(MV_MAX_SEG == 3, "locate() is written out for three segments");
+    if (tile < tiles[0]) return 0;
+    tile -= tiles[0];
+    if (tile < tiles[1]) return 1;
+    tile -= tiles[1];
+    return 2;
+  }
+  // first tile of CTA c of G: the tile at which the cumulative cost reaches c/G of the total
+  __host__ __device__ __forceinline__ int boundary(int c, int G) const {
+    if (c >= G) return ntiles;
+    long target = total * c / G;
+    int base = 0;
+#pragma unroll
+    for (int s = 0; s < MV_MAX_SEG; s++) {
+      const long span = (long)tiles[s] * cost[s];
+      if (target < span || s == MV_MAX_SEG - 1) return base + (int)min((long)tiles[s], (target + cost[s] / 2) / cost[s]);
+      target -= span; base += tiles[s];
+    }
+    return ntiles;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Phases of a step
+enum : int { PH_MATVEC = 0, PH_ATTN = 1, PH_EMBED = 2, PH_PICK = 3 };
+struct EmbedParams { const uint8_t* table; size_t row_bytes; const int* tokens; float* out; int type, K, n_vocab; };
+struct PickParams { const float* logits; int* state; int* out_tokens; int n; };
+struct alignas(16) Phase {
+  int kind;
+  int q6;           // PH_MATVEC: some matrix of the phase is Q6_K (the activation staging then also builds cneg)
+  MVParams mv;      // PH_MATVEC
+  AttnParams at;    // PH_ATTN
+  EmbedParams em;   // PH_EMBED
+  PickParams pk;    // PH_PICK
+};
+
+struct StepArgs {
+  const Phase* prog;
+  int n_phases;
+  int n_slots;
+  unsigned* sync;   // [0] grid-barrier arrivals, [1] finished CTAs (the last one resets both)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// what lane j knows about tile T0 + j of this CTA's range
+struct TileInfo { int seg, til, nch, type; };
+__device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParams& p, int tile, int nb, bool valid) {
+  TileInfo ti;
+  ti.seg = 0; ti.til = 0; ti.nch = 0; ti.type = GT_Q4_K;
+  if (valid) {
+    int tl = tile;
+    ti.seg = ts.locate(tl);
+    ti.til = tl;
+    ti.type = ti.seg == 0 ? p.seg[0].w.type : (ti.seg == 1 ? p.seg[1].w.type : p.seg[2].w.type);
+    const int kb = st_chunk_blocks(ti.type);
+    ti.nch = (nb + kb - 1) / kb;
+  }
+  return ti;
+}
+
+// Producer warp: the same enumeration as the consumers, one bulk copy per item, as far ahead as the ring allows.
+__device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t S = (uint32_t)args.n_slots;
+  uint32_t seq = 0;
+  for (int ip = 0; ip < args.n_phases; ip++) {
+    const Phase* ph = args.prog + ip;
+    if (ph->kind != PH_MATVEC) continue;
+    const MVParams& p = ph->mv;
+    TileSpace ts;
+    ts.init(p);
+    const int T0 = ts.boundary(blockIdx.x, gridDim.x), T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
+    const int nb = p.K >> 8;
+    for (int w0 = T0; w0 < T1; w0 += ST_MAXT) {
+      const int ntw = min(ST_MAXT, T1 - w0);
+      const TileInfo ti = tile_info(ts, p, w0 + lane, nb, lane < ntw);
+      for (int kc = 0;; kc++) {
+        unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
+        if (!mask) break;
+        while (mask) {
+          const int j = __ffs(mask) - 1;
+          mask &= mask - 1;
+          const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
+          if (lane == 0) {
+            const int kb = st_chunk_blocks(type), bb = st_block_bytes(type);
+            const int nblk = min(kb, nb - kc * kb);
+            const uint8_t* base = seg == 0 ? p.seg[0].w.st : (seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
+            const uint8_t* src = base + ((size_t)til * nb + (size_t)kc * kb) * bb;
+            const uint32_t slot = seq % S, bytes = (uint32_t)(nblk * bb);
+            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+            mbar_expect_tx(&full_bar[slot], bytes);
+            bulk_g2s(ring + (size_t)slot * ST_SLOT, src, bytes, &full_bar[slot]);
+          }
+          seq++;
+        }
+      }
+    }
+  }
+}
+
+// Consumer side of one mat-vec phase.  `seq` is the running item number (identical in every warp and in the producer).
+__device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& np, uint8_t* ring, uint8_t* act_smem, double* red, uint64_t* full_bar, uint64_t* empty_bar,
+                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq) {
+  const MVParams& p = ph.mv;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0);
+  const StAct a = st_act_extras<ST_NT, ST_BAR>(act_smem, p.K, ph.q6 != 0);
+  TileSpace ts;
+  ts.init(p);
+  const int T0 = ts.boundary(blockIdx.x, gridDim.x), T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
+  const int nb = p.K >> 8;
+#pragma unroll 1
+  for (int w0 = T0; w0 < T1; w0 += ST_MAXT) {
+    if (w0 != T0) {   // the mailboxes are re-used by the next ST_MAXT tiles
+      bar_sync<ST_BAR, ST_NT>();
+      if (threadIdx.x < ST_MAXT) flags[threadIdx.x] = 0;
+      bar_sync<ST_BAR, ST_NT>();
+    }
+    const int ntw = min(ST_MAXT, T1 - w0);
+    const TileInfo ti = tile_info(ts, p, w0 + lane, nb, lane < ntw);
+#pragma unroll 1
+    for (int kc = 0;; kc++) {
+      const unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
+      if (!mask) break;
+      const int cnt = __popc(mask);
+#pragma unroll 1
+      for (int r = (int)(((uint32_t)warp + ST_W - seq % ST_W) % ST_W); r < cnt; r += ST_W) {
+        const int j = __fns(mask, 0, r + 1);
+        const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
+        const int nch = __shfl_sync(0xffffffffu, ti.nch, j);
+        const uint32_t n = seq + (uint32_t)r, slot = n % S;
+        const int kb = st_chunk_blocks(type);
+        const int b0 = kc * kb, nblk = min(kb, nb - b0);
+        const MVSeg& sg = p.seg[seg];
+        const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
+        mbar_wait(&full_bar[slot], (n / S) & 1u);
+        volatile float* mail = mailbox[j];
+        volatile int* flag = flags + j;
+        const bool last = kc == nch - 1;
+        if (type == GT_Q4_K) run_item<GT_Q4_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+        else if (type == GT_Q6_K) run_item<GT_Q6_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+        else run_item<GT_Q5_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+      }
+      seq += (uint32_t)cnt;
+    }
+  }
+}
+
+// greedy pick + state advance (k_argmax + k_advance of the un-fused path), CTA 0 only
+__device__ __forceinline__ void st_pick_phase(const PickParams& pk, float* bv, int* bi) {
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < pk.n; i += ST_NT) {
+    const float v = __ldcg(pk.logits + i);
+    if (v > best) { best = v; idx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+  bar_sync<ST_BAR, ST_NT>();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < ST_W; w++)
+      if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+    int* st = pk.state;   // {token, position, step, n_total, pick}
+    st[4] = idx;
+    pk.out_tokens[st[2]] = idx;
+    st[0] = idx;
+    st[1] += 1;
+    st[2] += 1;
+    st[3] = st[1] + 1;
+  }
+}
+
+static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_constant__ StepArgs args) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[ST_MAX_SLOTS];
+  __shared__ __align__(8) uint64_t empty_bar[ST_MAX_SLOTS];
+  __shared__ double red[ST_W];
+  __shared__ __align__(16) float mailbox[ST_MAXT][ST_STATE * 32];
+  __shared__ int flags[ST_MAXT];
+  __shared__ float pick_v[ST_W];
+  __shared__ int pick_i[ST_W];
+  __shared__ __align__(16) Phase ph;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* ring = smem;
+  uint8_t* act_smem = smem + (size_t)args.n_slots * ST_SLOT;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < args.n_slots; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_trigger();
+  if (warp == ST_W) {   // weights are constants of the model: the stream starts before the predecessor kernel has finished
+    st_producer(args, ring, full_bar, empty_bar);
+    return;
+  }
+  pdl_wait();
+  const unsigned G = gridDim.x;
+  uint32_t seq = 0;
+#pragma unroll 1
+  for (int ip = 0; ip < args.n_phases; ip++) {
+    bar_sync<ST_BAR, ST_NT>();                 // every consumer warp is done with the previous phase (its stores are issued)
+    if (threadIdx.x == 0 && ip > 0) { __threadfence(); atomicAdd(args.sync, 1u); }
+    {   // next phase descriptor → shared memory; fold flags cleared
+      const uint4* src = (const uint4*)(args.prog + ip);
+      uint4* dst = (uint4*)&ph;
+      for (int i = threadIdx.x - 32; i >= 0 && i < (int)(sizeof(Phase) / 16); i += ST_NT - 32) dst[i] = __ldg(src + i);
+      if (threadIdx.x < ST_MAXT) flags[threadIdx.x] = 0;
+    }
+    bar_sync<ST_BAR, ST_NT>();
+    NormPre np;
+    if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);   // constants: fetched while the barrier completes
+    if (threadIdx.x == 0 && ip > 0) {
+      const unsigned target = (unsigned)ip * G;
+      while (ld_acquire_u32(args.sync) < target) { }
+    }
+    bar_sync<ST_BAR, ST_NT>();
+    if (ph.kind == PH_MATVEC) {
+      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq);
+    } else if (ph.kind == PH_ATTN) {
+      const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
+      for (int task = blockIdx.x; task < n_tasks; task += G) {
+        if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
+        attn_body<ST_NT, ST_BAR, false>(ph.at, act_smem, task / n_cg, 0, task % n_cg);
+      }
+    } else if (ph.kind == PH_EMBED) {
+      if (blockIdx.x == 0) {
+        const int tok = ph.em.tokens[0];
+        const uint8_t* row = ph.em.table + (size_t)min(max(tok, 0), ph.em.n_vocab - 1) * ph.em.row_bytes;
+        for (int e = threadIdx.x; e < ph.em.K; e += ST_NT) ph.em.out[e] = dequant_elem(ph.em.type, row, e);
+      }
+    } else if (ph.kind == PH_PICK) {
+      if (blockIdx.x == 0) st_pick_phase(ph.pk, pick_v, pick_i);
+    }
+  }
+  bar_sync<ST_BAR, ST_NT>();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(args.sync + 1, 1u) == G - 1) {   // every CTA is past its last barrier: re-arm for the next launch
+      args.sync[0] = 0u;
+      args.sync[1] = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+struct StepLaunch { int grid; int n_slots; size_t smem; };
+
+// shared-memory budget: ring slots fill what the largest activation image of the program leaves
+inline StepLaunch step_launch_shape(const Phase* phases, int n, int n_sm, size_t max_dyn_smem, size_t extra_act = 0) {
+  size_t act = extra_act;
+  for (int i = 0; i < n; i++) {
+    if (phases[i].kind == PH_MATVEC) act = std::max(act, st_act_bytes(phases[i].mv.K, phases[i].q6 != 0));
+    if (phases[i].kind == PH_ATTN) act = std::max(act, attn_smem_bytes(phases[i].at.n_ctx, phases[i].at.hd));
+  }
+  act = (act + 127) & ~(size_t)127;
+  StepLaunch L;
+  L.grid = n_sm;
+  if (act + 2 * (size_t)ST_SLOT > max_dyn_smem) { L.n_slots = 0; L.smem = 0; return L; }
+  L.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (max_dyn_smem - act) / ST_SLOT);
+  L.smem = (size_t)L.n_slots * ST_SLOT + act;
+  return L;
+}
+
+// a mat-vec phase the step kernel can run: all matrices K-quant (→ Q8_K activations), K a multiple of 256
+inline bool step_supports(const MVParams& p) {
+  if (p.K % 256) return false;
+  for (int s = 0; s < p.nseg; s++)
+    if (!type_is_kquant(p.seg[s].w.type) || !p.seg[s].w.st) return false;
+  return p.nseg >= 1;
+}
+inline Phase matvec_phase(const MVParams& p) {
+  Phase ph{};
+  ph.kind = PH_MATVEC;
+  ph.mv = p;
+  ph.mv.act = ACT_Q8_K;
+  for (int s = 0; s < p.nseg; s++) ph.q6 |= p.seg[s].w.type == GT_Q6_K;
+  return ph;
+}
+
+static inline size_t step_max_dyn_smem() {
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, k_step) != cudaSuccess) return 0;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  return (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
+}
+static inline cudaError_t step_set_smem_limit(size_t bytes) { return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+
+static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, int n_phases, unsigned* d_sync, bool pdl = false) {
+  StepArgs a;
+  a.prog = d_prog; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_step, a);
+}
+
+}  // namespace ctb

@@ -65,7 +65,6 @@ EXTRA_PROTOTYPES = {
     "ctb_llm_set_stream": (None, [_P, C.c_void_p]),
     "ctb_llm_decode_greedy": (C.c_double, [_P, C.c_int, C.c_int, C.c_int, _IP]),
     "ctb_llm_profile_step": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _IP]),
-    "ctb_llm_trace_step": (C.c_long, [_P, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_long]),
     "ctb_llm_time_matvec_only": (C.c_double, [_P, C.c_int, C.POINTER(C.c_long)]),
     "ctb_llm_time_matvec_kinds": (C.c_double, [_P, C.c_int, C.POINTER(C.c_long), C.c_uint]),
     "ctb_mul_mat": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_int, C.c_int]),

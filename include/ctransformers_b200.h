@@ -59,7 +59,7 @@ void ctransformers_llm_reset(LLM* llm);                     /* llm.cc:134 */
 /* ------------------------------------------------------------------ part 2: additive ---------- */
 int ctb_abi_version(void);
 double ctb_llm_last_eval_ms(LLM* llm);              /* CUDA-event time of the last batch_eval / decode_greedy */
-long ctb_llm_launches_per_token(LLM* llm);          /* kernels in one decode step's CUDA graph */
+long ctb_llm_launches_per_token(LLM* llm);          /* kernels in one decode step's CUDA graph (a K-quant model: 1, the persistent step kernel) */
 /* batch_eval calls answered by the step the engine had already started for the greedy next token (engine.cu: after_eval);
  * CTB_NO_SPEC=1 in the environment turns that look-ahead off. */
 long ctb_llm_speculative_hits(LLM* llm);
@@ -69,15 +69,12 @@ void ctb_llm_set_stream(LLM* llm, void* cuda_stream);        /* run on a caller-
  * returns the device-timed milliseconds, < 0 on error.  Logits of the last step land in logits_data. */
 double ctb_llm_decode_greedy(LLM* llm, int first_token, int n_past, int n_steps, int* out_tokens);
 
-/* One eager decode step with a CUDA event after every kernel; ADDS device milliseconds and launch counts per class into
+/* One eager decode step, one kernel per op (un-fused), with a CUDA event after every kernel; ADDS device milliseconds and launch counts per class into
  * ms_by_kind[4] / count_by_kind[4] (0 mat-vec, 1 attention, 2 rope+kv store, 3 other).  Returns kernels timed, < 0 on error. */
 int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, int* count_by_kind);
-/* The mat-vec launches of one decode step alone (same kernels, parameters and order; attention, embedding and argmax left
+/* The mat-vec phases of one decode step alone (same kernel, parameters and order; attention, embedding and pick left
  * out), replayed reps times as a CUDA graph between two CUDA events: returns milliseconds per step, < 0 on error;
- * *launches = mat-vec launches per step.  KV cache and logits are not meaningful afterwards. */
-/* One decode step as a CUDA graph whose k_matvec CTAs stamp %globaltimer (ns): per launch out holds {kind, n_cta} and, per CTA,
- * {entry, dependency released, input staged, 0, end of warp 0..15}.  Returns the launches written, or -(words needed). */
-long ctb_llm_trace_step(LLM* llm, int token, int n_past, unsigned long long* out, long cap_words);
+ * *launches = mat-vec phases per step.  KV cache and logits are not meaningful afterwards. */
 double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches);
 /* Same, restricted to the launches whose kind bit is set in kind_mask (bit 0 QKV, 1 attention output, 2 FFN gate+up,
  * 3 FFN down, 4 output head; 0 = all): per-projection timing under in-graph launch conditions. */
@@ -115,9 +112,9 @@ int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache
 /* silu(W1 x) * (W3 x) with the fp16 SiLU table (ggml.c:3625-3632) — the fused FFN gate. */
 int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const float* x, float* out, int K, int M);
 /* ggml_get_rows on a quantized table (ggml.c:11615-11642). */
-/* How a K-quant mat-vec launch over nseg matrices (types[], rows[], all K wide) is cut up on a GPU with n_sm SMs — pure host
- * arithmetic, no device needed: first_tile[0..grid] = first 8-row tile of each CTA (cost-balanced), meta = {grid, dynamic
- * shared bytes, parked blocks per warp, tiles, warps per CTA, rows per tile, shared-memory limit}.  0 on success. */
+/* How a K-quant mat-vec phase over nseg matrices (types[], rows[], all K wide) is cut up on a GPU with n_sm SMs — pure host
+ * arithmetic, no device needed: first_tile[0..grid] = first 16-row tile of each CTA (byte-balanced), meta = {grid, ring slot
+ * bytes, tiles alive per CTA (mailboxes), tiles, consumer warps per CTA, rows per tile, work items of the largest CTA}.  0 on success. */
 int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int n_sm, int* first_tile, int* meta);
 
 int ctb_get_row(int type, const void* table_blocks, int K, int n_rows, int row, float* out);

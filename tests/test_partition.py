@@ -1,12 +1,14 @@
-"""Host-side check (no GPU) of how k_matvec cuts a K-quant launch into per-CTA tile ranges and per-warp block ranges
-(csrc/matvec.cuh: TileSpace, matvec_launch_shape), through ctb_matvec_partition.  The device code uses the same functions."""
+"""Host-side check (no GPU) of how the step kernel cuts a K-quant mat-vec phase into per-CTA 16-row tile ranges and work items
+(csrc/stream.cuh: TileSpace, st_chunk_blocks), through ctb_matvec_partition.  The device code uses the same functions."""
 import ctypes as C
 
 import numpy as np
 import pytest
 
 Q4_K, Q5_K, Q6_K = 12, 13, 14
-COST = {Q4_K: 9, Q5_K: 11, Q6_K: 13}     # relative cost of a tile = bytes per block / 16
+COST = {Q4_K: 72, Q5_K: 88, Q6_K: 105}     # relative cost of a tile = bytes per row-block / 2
+CHUNK = {Q4_K: 4, Q5_K: 3, Q6_K: 3}        # blocks per work item (one ring slot)
+BLOCK_BYTES = {Q4_K: 144, Q5_K: 176, Q6_K: 210}
 
 SHAPES = [
     # (name, K, [(type, rows), ...])
@@ -32,16 +34,17 @@ def partition(lib, K, segs, n_sm=148):
     meta = (C.c_int * 8)()
     assert lib.ctb_matvec_partition(types, rows, len(segs), K, n_sm, first, meta) == 0
     grid = meta[0]
-    return list(first[:grid + 1]), dict(grid=grid, smem=meta[1], def_max=meta[2], tiles=meta[3], warps=meta[4], rows_per_tile=meta[5], smem_limit=meta[6])
+    return list(first[:grid + 1]), dict(grid=grid, slot=meta[1], alive=meta[2], tiles=meta[3], warps=meta[4], rows_per_tile=meta[5], max_items=meta[6])
 
 
 @pytest.mark.parametrize("name,K,segs", SHAPES, ids=[s[0] for s in SHAPES])
-def test_cta_ranges_cover_all_tiles_in_order_and_are_cost_balanced(lib, name, K, segs):
+def test_cta_ranges_cover_all_tiles_in_order_and_are_byte_balanced(lib, name, K, segs):
     first, m = partition(lib, K, segs)
     rpt = m["rows_per_tile"]
+    assert rpt == 16
     tiles = [(rows + rpt - 1) // rpt for _, rows in segs]
     assert m["tiles"] == sum(tiles)
-    assert 1 <= m["grid"] <= 148 and m["grid"] <= m["tiles"]
+    assert m["grid"] == 148
     assert first[0] == 0 and first[-1] == m["tiles"]
     assert all(a <= b for a, b in zip(first, first[1:])), "CTA ranges must be contiguous and ordered"
     # cumulative cost at every boundary is within one tile of the ideal split
@@ -50,31 +53,27 @@ def test_cta_ranges_cover_all_tiles_in_order_and_are_cost_balanced(lib, name, K,
     total = cum[-1]
     for c, t in enumerate(first):
         assert abs(cum[t] - total * c / m["grid"]) <= max(COST.values()), (c, t)
-    # shared memory: fits the limit, and the parked-terms buffer is at least one block deep
-    assert m["smem"] <= m["smem_limit"] and m["def_max"] >= 1
 
 
 @pytest.mark.parametrize("name,K,segs", SHAPES, ids=[s[0] for s in SHAPES])
-def test_warp_ranges_are_equal_and_parking_covers_every_mid_row_segment(lib, name, K, segs):
-    """Inside a CTA the blocks of its tiles are cut into `warps` equal contiguous ranges; a range that starts inside a row
-    parks at most def_max blocks before it needs its predecessor's state — for the shapes of the bench models the whole
-    segment fits (no serialised chain)."""
+def test_work_items_fit_a_ring_slot_and_match_the_device_enumeration(lib, name, K, segs):
+    """A work item = one 16-row tile x CHUNK[type] blocks; it must fit one ring slot, and the largest CTA's item count the
+    library reports must equal the count from walking the tiles here."""
     first, m = partition(lib, K, segs)
-    nb, W = K // 256, m["warps"]
-    worst_unparked = 0
+    nb = K // 256
+    for t in (Q4_K, Q5_K, Q6_K):
+        assert 16 * BLOCK_BYTES[t] * CHUNK[t] <= m["slot"]
+        assert (16 * BLOCK_BYTES[t]) % 16 == 0      # cp.async.bulk: 16-byte granularity
+    type_of_tile = []
+    for t, rows in segs:
+        type_of_tile += [t] * ((rows + 15) // 16)
+    worst = 0
     for t0, t1 in zip(first, first[1:]):
-        B = (t1 - t0) * nb
-        L = -(-B // W) if B else 0
-        covered = 0
-        for w in range(W):
-            s0, e0 = min(B, w * L), min(B, w * L + L)
-            covered += e0 - s0
-            a0 = s0 % nb
-            mid_len = min(nb - a0, e0 - s0) if a0 else 0
-            worst_unparked = max(worst_unparked, mid_len - m["def_max"])
-        assert covered == B
-    if name.startswith(("7b", "13b")):
-        assert worst_unparked <= 0, f"a mid-row segment of {worst_unparked + m['def_max']} blocks does not fit the parking buffer"
+        worst = max(worst, sum(-(-nb // CHUNK[type_of_tile[i]]) for i in range(t0, t1)))
+    assert worst == m["max_items"]
+    if name.startswith(("7b", "13b", "falcon")):
+        # the fold chains of all tiles of a CTA are alive together: one mailbox each
+        assert max(b - a for a, b in zip(first, first[1:])) <= 2 * m["alive"]
 
 
 def test_rejects_what_the_kernel_cannot_run(lib):
