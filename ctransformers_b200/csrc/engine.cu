@@ -2,6 +2,7 @@
 #include "engine.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -42,14 +43,11 @@ __global__ void k_advance(int* state, int* out_tokens) {
   state[3] = state[1] + 1;   // a single-token eval: the attention rows have length position + 1
 }
 
+constexpr size_t UP_CHUNK = (size_t)32 << 20;   // upload pipeline: chunk bytes and buffers in flight
+constexpr int UP_BUFS = 3;
+
 static bool supported_matrix_type(uint32_t t) {
   return t == T_F32 || t == T_F16 || t == T_Q4_0 || t == T_Q8_0 || t == T_Q4_K || t == T_Q5_K || t == T_Q6_K;
-}
-
-static size_t max_raw_tensor_bytes(const GGUFFile& g) {
-  size_t m = 0;
-  for (const auto& t : g.tensors) m = std::max(m, (size_t)t.nbytes);
-  return m;
 }
 
 size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
@@ -58,7 +56,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
     total += align_up(t.nbytes, 256) + 4 * 256;   // up to 4 planes, each 256-aligned
     if (t.ne[1] > 0) total += align_up(t.nbytes / (size_t)t.ne[1] * ST_ROWS, 256);   // K-quants: rows padded to whole 16-row tiles
   }
-  total += align_up(max_raw_tensor_bytes(g), 256);                              // raw staging for the repack
+  total += UP_CHUNK * UP_BUFS + 256;                                            // device staging of the upload pipeline
   const size_t kv = (size_t)hp.n_layer * (hp.n_ctx + 256) * hp.n_embd_gqa() * 2;
   total += 2 * align_up(kv, 256);
   total += 3 * align_up(65536 * 2, 256);
@@ -77,7 +75,49 @@ void* Engine::alloc(size_t bytes, size_t align) {
   return arena_ + off;
 }
 
-DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging, int want_K, int want_M) {
+// ---- load pipeline (reference: llama_model_loader::load_all_data, llama.cpp:1417-1487 + ggml_cuda_transform_tensor,
+// ggml-cuda.cu:6359-6432 — a blocking cudaMemcpy per tensor).  Here a tensor travels in row chunks of <= UP_CHUNK bytes through
+// UP_BUFS pinned host buffers and as many device staging buffers: the host thread copies chunk i+1 out of the mmap'ed file
+// into pinned memory while chunk i is on the wire (cudaMemcpyAsync from pinned memory is truly asynchronous) and chunk i-1 is
+// being repacked on the GPU; buffers are recycled behind events, nothing synchronises per tensor.
+struct Uploader {
+  uint8_t* host[UP_BUFS] = {nullptr, nullptr, nullptr};
+  uint8_t* dev[UP_BUFS] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done[UP_BUFS] = {nullptr, nullptr, nullptr};
+  cudaStream_t st[UP_BUFS] = {nullptr, nullptr, nullptr};
+  int next = 0;
+  size_t bytes = 0;
+  void init(uint8_t* dev_base) {
+    for (int i = 0; i < UP_BUFS; i++) {
+      CTB_CUDA(cudaMallocHost(&host[i], UP_CHUNK));
+      dev[i] = dev_base + (size_t)i * UP_CHUNK;
+      CTB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+      CTB_CUDA(cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking));
+    }
+  }
+  // copies [src, src+n) to the device staging buffer of the next slot; returns the slot (its stream carries the copy)
+  int push(const uint8_t* src, size_t n) {
+    const int i = next;
+    next = (next + 1) % UP_BUFS;
+    CTB_CUDA(cudaEventSynchronize(done[i]));        // the slot's previous chunk has been repacked
+    memcpy(host[i], src, n);
+    CTB_CUDA(cudaMemcpyAsync(dev[i], host[i], n, cudaMemcpyHostToDevice, st[i]));
+    bytes += n;
+    return i;
+  }
+  void finish(int i) { CTB_CUDA(cudaEventRecord(done[i], st[i])); }
+  void drain() { for (int i = 0; i < UP_BUFS; i++) if (st[i]) CTB_CUDA(cudaStreamSynchronize(st[i])); }
+  void release() {
+    for (int i = 0; i < UP_BUFS; i++) {
+      if (st[i]) { cudaStreamSynchronize(st[i]); cudaStreamDestroy(st[i]); }
+      if (done[i]) cudaEventDestroy(done[i]);
+      if (host[i]) cudaFreeHost(host[i]);
+      st[i] = nullptr; done[i] = nullptr; host[i] = nullptr;
+    }
+  }
+};
+
+DevMat Engine::upload_matrix(const GGUFTensor& t, Uploader& up, int want_K, int want_M) {
   if (!supported_matrix_type(t.type)) throw std::runtime_error("tensor '" + t.name + "': quantization type " + std::to_string(t.type) + " is not supported by the B200 path");
   DevMat m;
   m.type = (int)t.type;
@@ -89,29 +129,38 @@ DevMat Engine::upload_matrix(const GGUFTensor& t, uint8_t* staging, int want_K, 
                              std::to_string(m.K) + " x " + std::to_string(m.M));
   m.nb = m.K / type_block_elems(t.type);
   m.bytes = t.nbytes;
-  CTB_CUDA(cudaMemcpyAsync(staging, t.data, t.nbytes, cudaMemcpyHostToDevice, stream_));
-  if (type_is_kquant(m.type)) {
-    const size_t sb = st_matrix_bytes(m.type, m.M, m.nb);
-    uint16_t* st = (uint16_t*)alloc(sb);
-    const int grid = (int)std::min<size_t>((sb / 2 + 255) / 256, (size_t)sm_count_ * 32);
-    k_repack_stream<<<grid, 256, 0, stream_>>>(m.type, staging, m.M, m.nb, st);
-    CTB_CUDA(cudaGetLastError());
-    CTB_CUDA(cudaStreamSynchronize(stream_));   // staging is reused by the next tensor
+  const size_t row_bytes = t.nbytes / (size_t)m.M;
+  int rows_per_chunk = (int)std::max<size_t>(ST_ROWS, UP_CHUNK / row_bytes / ST_ROWS * ST_ROWS);   // whole 16-row tiles
+  if (row_bytes * ST_ROWS > UP_CHUNK) throw std::runtime_error("tensor '" + t.name + "': rows too long for the upload staging buffers");
+  uint16_t *st = nullptr, *qs = nullptr, *d = nullptr;
+  const bool kq = type_is_kquant(m.type);
+  if (kq) {
+    st = (uint16_t*)alloc(st_matrix_bytes(m.type, m.M, m.nb));
     m.st = (const uint8_t*)st;
-    return m;
+  } else {
+    const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, t.nbytes);
+    qs = (uint16_t*)alloc(ps.qs);
+    if (ps.d) d = (uint16_t*)alloc(ps.d);
+    m.qs = (const uint8_t*)qs; m.d = d;
   }
-  uint16_t *qs = nullptr, *qh = nullptr, *sc = nullptr, *d = nullptr;
-  const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, t.nbytes);
-  qs = (uint16_t*)alloc(ps.qs);
-  if (ps.qh) qh = (uint16_t*)alloc(ps.qh);
-  if (ps.sc) sc = (uint16_t*)alloc(ps.sc);
-  if (ps.d) d = (uint16_t*)alloc(ps.d);
-  const size_t n_u16 = t.nbytes / 2;
-  const int grid = (int)std::min<size_t>((n_u16 + 255) / 256, (size_t)sm_count_ * 32);
-  k_repack<<<grid, 256, 0, stream_>>>(m.type, (const uint16_t*)staging, n_u16, qs, qh, sc, d);
-  CTB_CUDA(cudaGetLastError());
-  CTB_CUDA(cudaStreamSynchronize(stream_));   // staging is reused by the next tensor
-  m.qs = (const uint8_t*)qs; m.qh = (const uint8_t*)qh; m.sc = (const uint8_t*)sc; m.d = d;
+  for (int r0 = 0; r0 < m.M; r0 += rows_per_chunk) {
+    const int rows = std::min(rows_per_chunk, m.M - r0);
+    const size_t n = (size_t)rows * row_bytes;
+    const int slot = up.push(t.data + (size_t)r0 * row_bytes, n);
+    if (kq) {
+      const size_t sb = st_matrix_bytes(m.type, rows, m.nb);
+      const int grid = (int)std::min<size_t>((sb / 2 + 255) / 256, (size_t)sm_count_ * 32);
+      k_repack_stream<<<grid, 256, 0, up.st[slot]>>>(m.type, up.dev[slot], rows, m.nb, st + (size_t)(r0 / ST_ROWS) * m.nb * st_block_bytes(m.type) / 2);
+    } else {
+      const size_t n_u16 = n / 2;
+      const size_t blk0 = (size_t)r0 * m.nb;
+      const int grid = (int)std::min<size_t>((n_u16 + 255) / 256, (size_t)sm_count_ * 32);
+      uint16_t* qdst = qs + (m.type == GT_Q4_0 ? blk0 * 8 : (m.type == GT_Q8_0 ? blk0 * 16 : (size_t)r0 * row_bytes / 2));
+      k_repack<<<grid, 256, 0, up.st[slot]>>>(m.type, (const uint16_t*)up.dev[slot], n_u16, qdst, nullptr, nullptr, d ? d + blk0 : nullptr);
+    }
+    CTB_CUDA(cudaGetLastError());
+    up.finish(slot);
+  }
   return m;
 }
 
@@ -183,7 +232,10 @@ void Engine::init(const GGUFFile& g) {
 
   arena_size_ = engine_arena_bytes(g, hp_);
   CTB_CUDA(cudaMalloc(&arena_, arena_size_));
-  uint8_t* staging = (uint8_t*)alloc(align_up(max_raw_tensor_bytes(g), 256));
+  const auto t_load0 = std::chrono::steady_clock::now();
+  Uploader up;
+  struct UpGuard { Uploader& u; ~UpGuard() { u.release(); } } up_guard{up};
+  up.init((uint8_t*)alloc(UP_CHUNK * UP_BUFS));
 
   // ---- weights (shapes follow from the hyper-parameters: llama.cpp:1878-1934 llama, 1948-2012 falcon)
   const std::string pfx = "blk.";
@@ -199,7 +251,7 @@ void Engine::init(const GGUFFile& g) {
   }
   out_norm_ = upload_vector(g, "output_norm.weight", true, n_embd);
   out_norm_b_ = upload_vector(g, "output_norm.bias", hp_.falcon, n_embd);
-  output_ = upload_matrix(g.need_tensor("output.weight"), staging, n_embd, hp_.n_vocab);
+  output_ = upload_matrix(g.need_tensor("output.weight"), up, n_embd, hp_.n_vocab);
   size_t wbytes = output_.bytes;
   layers_.resize(hp_.n_layer);
   for (int il = 0; il < hp_.n_layer; il++) {
@@ -210,25 +262,28 @@ void Engine::init(const GGUFFile& g) {
       L.attn_norm_b = upload_vector(g, b + "attn_norm.bias", true, n_embd);
       L.attn_norm2 = upload_vector(g, b + "attn_norm_2.weight", false, n_embd);
       if (L.attn_norm2) L.attn_norm2_b = upload_vector(g, b + "attn_norm_2.bias", true, n_embd);
-      L.wqkv = upload_matrix(g.need_tensor(b + "attn_qkv.weight"), staging, n_embd, n_embd + 2 * gqa);
-      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging, n_embd, n_embd);
-      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging, n_embd, n_ff);
-      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging, n_ff, n_embd);
+      L.wqkv = upload_matrix(g.need_tensor(b + "attn_qkv.weight"), up, n_embd, n_embd + 2 * gqa);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), up, n_embd, n_embd);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), up, n_embd, n_ff);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), up, n_ff, n_embd);
       wbytes += L.wqkv.bytes + L.wo.bytes + L.w3.bytes + L.w2.bytes;
     } else {
       L.ffn_norm = upload_vector(g, b + "ffn_norm.weight", true, n_embd);
-      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), staging, n_embd, n_embd);
-      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), staging, n_embd, gqa);
-      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), staging, n_embd, gqa);
-      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), staging, n_embd, n_embd);
-      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), staging, n_embd, n_ff);
-      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), staging, n_ff, n_embd);
-      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), staging, n_embd, n_ff);
+      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), up, n_embd, n_embd);
+      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), up, n_embd, gqa);
+      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), up, n_embd, gqa);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), up, n_embd, n_embd);
+      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), up, n_embd, n_ff);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), up, n_ff, n_embd);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), up, n_embd, n_ff);
       wbytes += L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.w1.bytes + L.w2.bytes + L.w3.bytes;
       if (act_format_for(L.w1.type) != act_format_for(L.w3.type)) throw std::runtime_error("ffn_gate / ffn_up use incompatible quantization families");
     }
   }
   stats.weight_bytes_per_token = wbytes;
+  up.drain();
+  stats.load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load0).count();
+  stats.load_bytes = up.bytes;
 
   // ---- lookup tables, built with the host libm exactly like ggml_init does (ggml.c:4319-4333)
   {

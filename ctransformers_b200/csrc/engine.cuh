@@ -37,8 +37,9 @@ struct LayerW {
 struct Phase;    // stream.cuh: one phase of the persistent step kernel
 struct StepOp;   // engine.cu: one op of the per-token schedule
 struct MVParams;
+struct Uploader;
 
-struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; long spec_hits = 0; };
+struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; long spec_hits = 0; double load_ms = 0; size_t load_bytes = 0; };
 
 class Engine {
  public:
@@ -106,7 +107,7 @@ class Engine {
 
   void init(const GGUFFile& g);
   void release();
-  DevMat upload_matrix(const GGUFTensor& t, uint8_t* staging, int want_K, int want_M);
+  DevMat upload_matrix(const GGUFTensor& t, struct Uploader& up, int want_K, int want_M);
   const float* upload_vector(const GGUFFile& g, const std::string& name, bool required, int want_n);
   // the per-token schedule
   std::vector<StepOp> ops_;      // EMBED, layers..., HEAD, PICK

@@ -175,6 +175,7 @@ double ctb_llm_last_eval_ms(LLM* llm) { return llm->engine->stats.last_eval_ms; 
 long ctb_llm_launches_per_token(LLM* llm) { return llm->engine->stats.launches; }
 long ctb_llm_speculative_hits(LLM* llm) { return llm->engine->stats.spec_hits; }
 unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm) { return (unsigned long long)llm->engine->stats.weight_bytes_per_token; }
+double ctb_llm_load_ms(LLM* llm) { return llm->engine->stats.load_ms; }
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream) { llm->engine->set_stream((cudaStream_t)cuda_stream); }
 
 double ctb_llm_decode_greedy(LLM* llm, int first_token, int n_past, int n_steps, int* out_tokens) {

@@ -64,6 +64,8 @@ long ctb_llm_launches_per_token(LLM* llm);          /* kernels in one decode ste
  * CTB_NO_SPEC=1 in the environment turns that look-ahead off. */
 long ctb_llm_speculative_hits(LLM* llm);
 unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm); /* algorithmic weight bytes one decode step reads */
+/* wall-clock milliseconds the weight upload took (mmap -> pinned staging -> H2D -> repack, pipelined; engine.cu Uploader) */
+double ctb_llm_load_ms(LLM* llm);
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream);        /* run on a caller-owned cudaStream_t */
 /* n_steps greedy decode steps with the token fed back on the device (no host round trip per token);
  * returns the device-timed milliseconds, < 0 on error.  Logits of the last step land in logits_data. */

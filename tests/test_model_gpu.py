@@ -177,3 +177,25 @@ def test_greedy_lookahead_hits_and_misses_match_the_oracle(model_dir, lib):
         llm.eval([tok])
         want = orc.eval([tok]).copy()
     assert llm.ctb_llm_speculative_hits() - hits0 >= 4
+
+
+# ---- BASELINE-size models (configs[1] and configs[3]) against the live reference: the same files bench.py times
+@pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("workload", ["llama2-7b", "falcon7b"])
+def test_bench_model_against_live_reference(workload):
+    """32-token prompt (reference default chunking, batch_size 8) + 8 greedy steps on the 7B-shaped bench model: logits after
+    the prompt, the greedy tokens and the last logits must be the reference's, bit for bit."""
+    import os
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+    bench.WL = bench.WORKLOADS[workload]
+    path = bench.ensure_model(0, 1, lambda: None)          # /tmp/ctb_models (shared with bench.py on the same box)
+    prompt = bench.prompt_ids()[:32]
+    cores = os.cpu_count() or 1
+    ours = modelcases.run_greedy(load(path, 128), prompt, 8)
+    theirs = modelcases.run_greedy(load(path, 128, lib=str(refs.REF_SO), threads=min(16, cores)), prompt, 8)
+    same_bits(ours[0], theirs[0])
+    same_bits(ours[1], theirs[1])
+    assert ours[2] == theirs[2]
+    same_bits(ours[3], theirs[3])
