@@ -190,21 +190,21 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 template <int BAR, int NT>
 __device__ __forceinline__ void attn_bar() { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); }
 
-// NT threads (barrier BAR) work on one (head, channel group) task.
+// NT threads (barrier BAR) work on one (query token n, head, channel group) task; q/k/v rows of token n are at n * stride.
 // PDLWAIT = true: a kernel of its own, q/k/v come from the previous kernel (griddepcontrol.wait after the prefetches).
 // PDLWAIT = false: a phase of the persistent step kernel (stream.cuh); the caller has already synchronised with the producers.
 template <int NT, int BAR, bool PDLWAIT>
-__device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, const int h, const int n, const int cg) {
+__device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, const int h, const int n, const int cg, const int* st) {
   constexpr int NW = NT / 32;
   __shared__ float red_f[NW];
   __shared__ double red_d[NW];
   const int hd = p.hd, per = hd >> 5;
   // Everything up to pdl_wait() reads only what earlier steps left behind (device state, RoPE table, cached K/V rows of
   // older positions): it overlaps the tail of the QKV kernel.  q/k/v of this token are read after the wait.
-  const int pos = p.state[1] + n;
+  const int pos = st[1];                 // st = {token, position, step, n_total} of query token n
   if (pos >= p.n_ctx) return;
   const int T = pos + 1;
-  const int n_total = max(T, min(p.state[3], p.n_ctx));
+  const int n_total = max(T, min(st[3], p.n_ctx));
   const int n_vec = n_total & ~31;
   const int group = p.n_head / p.n_kv, kvh = h / group;
   const bool kv_writer = (h % group) == 0;
@@ -399,7 +399,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
 static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   pdl_trigger();
-  attn_body<ATTN_THREADS, 0, true>(p, smem, blockIdx.x, blockIdx.y, blockIdx.z);
+  attn_body<ATTN_THREADS, 0, true>(p, smem, blockIdx.x, blockIdx.y, blockIdx.z, p.state);
 }
 
 // ----------------------------------------------------------------------------------------- argmax

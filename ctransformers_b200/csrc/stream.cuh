@@ -672,7 +672,7 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
       for (int task = blockIdx.x; task < n_tasks; task += G) {
         if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
-        attn_body<ST_NT, ST_BAR, false>(ph.at, act_smem, task / n_cg, 0, task % n_cg);
+        attn_body<ST_NT, ST_BAR, false>(ph.at, act_smem, task / n_cg, 0, task % n_cg, ph.at.state);
       }
     } else if (ph.kind == PH_EMBED) {
       if (blockIdx.x == 0) {
