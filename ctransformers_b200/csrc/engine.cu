@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "matvec.cuh"
+#include "prefill.cuh"
 #include "repack.cuh"
 #include "stream.cuh"
 #include "tables.hpp"
@@ -341,6 +342,8 @@ void Engine::init(const GGUFFile& g) {
   if (const char* e = getenv("CTB_NO_PDL")) pdl_ = !(e[0] == '1');
   if (const char* e = getenv("CTB_NO_SPEC")) spec_on_ = !(e[0] == '1');
   if (const char* e = getenv("CTB_STEP_FUSE")) fused_ = !(e[0] == '0');
+  if (const char* e = getenv("CTB_NO_PREFILL")) prefill_on_ = !(e[0] == '1');
+  if (const char* e = getenv("CTB_PREFILL_MIN")) prefill_min_ = std::max(1, atoi(e));
   CTB_CUDA(cudaMallocHost(&h_spec_tok_, 16));
   CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
@@ -354,6 +357,8 @@ void Engine::release() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   destroy_graphs();
+  delete pf_;
+  pf_ = nullptr;
   if (h_logits_) cudaFreeHost(h_logits_);
   if (h_embd_) cudaFreeHost(h_embd_);
   if (h_state_) cudaFreeHost(h_state_);
@@ -739,17 +744,41 @@ void Engine::after_eval(int next_pos) {
 
 void Engine::eval(const int* tokens, int n, int n_past) {
   if (n <= 0) return;
+  std::vector<int> pos(n), nt(n, n_past + n);   // n_total: row length of this eval's attention mat-muls
+  for (int i = 0; i < n; i++) pos[i] = n_past + i;
+  eval_list(tokens, pos.data(), nt.data(), n);
+}
+
+void Engine::decode_one(int token, int pos, int n_total, bool with_logits) {
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
+  int* st = h_state_ + (size_t)(h_state_next_ % h_state_cap_) * 4;
+  h_state_next_++;
+  st[0] = token; st[1] = pos; st[2] = 0; st[3] = n_total;
+  CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
+  CTB_CUDA(cudaGraphLaunch(with_logits ? graph_full_ : graph_nolog_, stream_));
+}
+
+void Engine::finish_eval(int next_pos, bool hit) {
+  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaEventRecord(ev1_, stream_));
+  after_eval(next_pos);
+  CTB_CUDA(cudaEventSynchronize(ev1_));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev0_, ev1_);
+  stats.last_eval_ms = ms;
+  stats.spec_hits += hit ? 1 : 0;
+}
+
+void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, int n) {
+  if (n <= 0) return;
   CTB_CUDA(cudaSetDevice(device_));
-  if (h_state_cap_ < n) {
-    if (h_state_) cudaFreeHost(h_state_);
-    h_state_cap_ = std::max(n, 512);
-    CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16));
-  }
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   bool hit = false;
   if (spec_pos_ >= 0) {
     const bool was_pending = spec_pending_;
     bool guessed = false;
-    if (n == 1 && n_past == spec_pos_) {
+    if (n == 1 && pos[0] == spec_pos_ && n_total[0] == pos[0] + 1) {
       CTB_CUDA(cudaEventSynchronize(ev_pick_));
       guessed = *h_spec_tok_ == tokens[0];
     }
@@ -760,22 +789,153 @@ void Engine::eval(const int* tokens, int n, int n_past) {
   }
   CTB_CUDA(cudaEventRecord(ev0_, stream_));
   if (!hit) {
-    for (int i = 0; i < n; i++) {
-      int* st = h_state_ + (size_t)i * 4;
-      st[0] = tokens[i]; st[1] = n_past + i; st[2] = 0; st[3] = n_past + n;   // n_total: row length of this eval's attention mat-muls
-      CTB_CUDA(cudaMemcpyAsync(d_state_, st, 16, cudaMemcpyHostToDevice, stream_));
-      CTB_CUDA(cudaGraphLaunch(i == n - 1 ? graph_full_ : graph_nolog_, stream_));
+    int i = 0;
+    while (i < n) {
+      // a run of consecutive positions goes through the batched kernel, PB_T tokens per launch
+      int j = i + 1;
+      while (j < n && pos[j] == pos[j - 1] + 1 && pos[j] < hp_.n_ctx) j++;
+      if (j - i >= prefill_min_ && pos[i] < hp_.n_ctx && ensure_prefill()) {
+        for (int b = i; b < j; b += PB_T) {
+          const int m = std::min(PB_T, j - b);
+          prefill_batch(tokens + b, pos + b, n_total + b, m, b + m == n);
+        }
+      } else {
+        for (int k = i; k < j; k++) {
+          decode_one(tokens[k], pos[k], n_total[k], k == n - 1);
+          if ((k - i) % 128 == 127) CTB_CUDA(cudaStreamSynchronize(stream_));   // keeps the pinned state ring from wrapping under the GPU
+        }
+      }
+      i = j;
     }
   }   // else: the step for this token at this position is already in the stream
-  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
-  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
-  CTB_CUDA(cudaEventRecord(ev1_, stream_));
-  after_eval(n_past + n);
-  CTB_CUDA(cudaEventSynchronize(ev1_));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, ev0_, ev1_);
-  stats.last_eval_ms = ms;
-  stats.spec_hits += hit ? 1 : 0;
+  finish_eval(pos[n - 1] + 1, hit);
+}
+
+// ---- batched prefill (prefill.cuh): the per-token schedule rewritten over PB_T-row buffers
+struct PrefillState {
+  std::vector<void*> bufs;          // cudaMalloc'ed
+  PPhase* d_prog = nullptr;
+  int n_phases = 0;
+  int* d_state = nullptr;           // [PB_T][4] + n_tok
+  int* h_state = nullptr;           // pinned, PF_RING launches deep
+  int h_next = 0;
+  float* x_final = nullptr;         // batched buffer that holds the last layer's output rows
+  int n_slots = 0;
+  size_t smem = 0;
+  bool ok = false, tried = false;
+  ~PrefillState() {
+    for (void* b : bufs) cudaFree(b);
+    if (h_state) cudaFreeHost(h_state);
+  }
+};
+constexpr int PF_RING = 64;
+
+bool Engine::ensure_prefill() {
+  if (!prefill_on_) return false;
+  if (pf_ && pf_->tried) return pf_->ok;
+  if (!pf_) pf_ = new PrefillState();
+  PrefillState& P = *pf_;
+  P.tried = true;
+  for (int i = 0; i < n_body_; i++)
+    if (ops_[i].ph.kind == PH_MATVEC && !ops_[i].stream) return false;   // a non-K-quant layer matrix: single-token path only
+  auto dalloc = [&](size_t bytes) {
+    void* p = nullptr;
+    CTB_CUDA(cudaMalloc(&p, bytes));
+    P.bufs.push_back(p);
+    CTB_CUDA(cudaMemset(p, 0, bytes));
+    return p;
+  };
+  const int n_embd = hp_.n_embd, gqa = hp_.n_embd_gqa();
+  const int qkvw = n_embd + 2 * gqa;
+  // decode buffer -> (batched buffer, floats between token rows)
+  struct Map { const float* lo; size_t n; float* b; int ld; };
+  std::vector<Map> maps;
+  auto add = [&](const float* dec, size_t n) { maps.push_back({dec, n, (float*)dalloc((size_t)PB_T * n * 4), (int)n}); };
+  add(xa_, n_embd); add(xb_, n_embd); add(qkv_, qkvw); add(attn_, n_embd); add(attn_o_, n_embd); add(ffn_, hp_.n_ff); add(ffn2_, hp_.n_ff);
+  auto bat = [&](const float* p, int& ld) -> float* {
+    if (!p) { ld = 0; return nullptr; }
+    for (const Map& m : maps)
+      if (p >= m.lo && p < m.lo + m.n) { ld = m.ld; return m.b + (p - m.lo); }
+    throw std::runtime_error("prefill: pointer outside the step workspace");
+  };
+  P.d_state = (int*)dalloc((PB_T * 4 + 4) * 4);
+  CTB_CUDA(cudaMallocHost(&P.h_state, (size_t)PF_RING * (PB_T * 4 + 4) * 4));
+  std::vector<PPhase> prog;
+  int K_max = 0;
+  for (int i = 0; i < n_body_; i++) {
+    const StepOp& op = ops_[i];
+    PPhase ph{};
+    ph.state = P.d_state;
+    if (op.ph.kind == PH_EMBED) {
+      ph.kind = PP_EMBED;
+      ph.em = op.ph.em;
+      int ld;
+      ph.em.out = bat(op.ph.em.out, ld);
+      prog.push_back(ph);
+    } else if (op.ph.kind == PH_ATTN) {
+      ph.at = op.ph.at;
+      int ld, ldo;
+      ph.at.q = bat(op.ph.at.q, ld); ph.at.k = bat(op.ph.at.k, ld); ph.at.v = bat(op.ph.at.v, ld);
+      ph.at.q_stride = ld; ph.at.kv_stride = ld;
+      ph.at.out = bat(op.ph.at.out, ldo);
+      ph.at.state = P.d_state;
+      ph.kind = PP_KV; prog.push_back(ph);
+      ph.kind = PP_ATTN; prog.push_back(ph);
+    } else {
+      const MVParams& m = op.ph.mv;
+      K_max = std::max(K_max, m.K);
+      ph.mv = m;
+      ph.mv.norm_out = nullptr;
+      ph.mv.x = bat(m.x, ph.x_ld);
+      ph.mv.x2 = bat(m.x2, ph.x2_ld);
+      ph.qbuf = (uint8_t*)dalloc(pb_qbuf_bytes(m.K));   // one buffer per phase: nothing stale can sit in an L1
+      ph.kind = PP_QUANT; prog.push_back(ph);
+      for (int sgi = 0; sgi < m.nseg; sgi++) {
+        ph.mv.seg[sgi].out = bat(m.seg[sgi].out, ph.out_ld[sgi]);
+        ph.mv.seg[sgi].res = bat(m.seg[sgi].res, ph.res_ld[sgi]);
+        ph.mv.seg[sgi].res2 = bat(m.seg[sgi].res2, ph.res2_ld[sgi]);
+      }
+      ph.kind = PP_GEMM; prog.push_back(ph);
+    }
+  }
+  int ld;
+  P.x_final = bat(ops_[n_body_].ph.mv.x, ld);
+  P.n_phases = (int)prog.size();
+  P.d_prog = (PPhase*)dalloc((prog.size() + 1) * sizeof(PPhase));
+  CTB_CUDA(cudaMemcpy(P.d_prog, prog.data(), prog.size() * sizeof(PPhase), cudaMemcpyHostToDevice));
+  const size_t work = pb_work_bytes(K_max, hp_.n_ctx, hp_.head_dim()), room = pstep_max_dyn_smem();
+  if (work + 4 * (size_t)ST_SLOT > room) return false;
+  P.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (room - work) / ST_SLOT);
+  P.smem = (size_t)P.n_slots * ST_SLOT + work;
+  CTB_CUDA(pstep_set_smem_limit(P.smem));
+  P.ok = true;
+  return true;
+}
+
+// n <= PB_T tokens at consecutive positions through all layers in one launch; `last`: the list ends here, so the head
+// mat-vec (logits + final-norm hidden state of the last token) follows on the single-token kernel.
+void Engine::prefill_batch(const int* tokens, const int* pos, const int* n_total, int n, bool last) {
+  PrefillState& P = *pf_;
+  if (P.h_next % PF_RING == PF_RING - 1) CTB_CUDA(cudaStreamSynchronize(stream_));   // pinned state ring
+  int* st = P.h_state + (size_t)(P.h_next++ % PF_RING) * (PB_T * 4 + 4);
+  for (int i = 0; i < PB_T; i++) {
+    const int k = std::min(i, n - 1);
+    st[i * 4] = tokens[k]; st[i * 4 + 1] = pos[k]; st[i * 4 + 2] = 0; st[i * 4 + 3] = n_total[k];
+  }
+  st[PB_T * 4] = n;
+  CTB_CUDA(cudaMemcpyAsync(P.d_state, st, (PB_T * 4 + 4) * 4, cudaMemcpyHostToDevice, stream_));
+  CTB_CUDA(launch_pstep(step_grid_, P.n_slots, P.smem, stream_, P.d_prog, P.n_phases, d_sync_));
+  if (last) {
+    const StepOp& head = ops_[n_body_];
+    CTB_CUDA(cudaMemcpyAsync(const_cast<float*>(head.ph.mv.x), P.x_final + (size_t)(n - 1) * hp_.n_embd, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
+    const bool keep = fused_;
+    fused_ = false;                                    // just this one op, the way the un-fused schedule launches it
+    std::vector<StepOp> one(1, head);
+    const long keepl = launches_per_step_;
+    try { enqueue_ops(one, d_prog_ + n_body_, 1); } catch (...) { fused_ = keep; throw; }
+    fused_ = keep;
+    launches_per_step_ = keepl;
+  }
 }
 
 double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens) {

@@ -38,6 +38,7 @@ struct Phase;    // stream.cuh: one phase of the persistent step kernel
 struct StepOp;   // engine.cu: one op of the per-token schedule
 struct MVParams;
 struct Uploader;
+struct PrefillState;
 
 struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_bytes_per_token = 0; long spec_hits = 0; double load_ms = 0; size_t load_bytes = 0; };
 
@@ -50,6 +51,9 @@ class Engine {
 
   // Evaluate n tokens starting at position n_past; afterwards logits()/embeddings() hold the last token's.
   void eval(const int* tokens, int n, int n_past);
+  // Evaluate a token list with explicit per-token position and n_total (= n_past + N of the reference eval call the token
+  // belongs to, llm.h:40-54): consecutive positions go through the batched prefill kernel, PB_T tokens per launch.
+  void eval_list(const int* tokens, const int* pos, const int* n_total, int n);
   // n_steps greedy decode steps entirely on the device stream (token feedback through k_argmax);
   // out_tokens[n_steps] receives the picked ids.  Returns device-timed milliseconds for the steps.
   double decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens);
@@ -91,6 +95,7 @@ class Engine {
   float *h_logits_ = nullptr, *h_embd_ = nullptr;
   int* h_state_ = nullptr;     // pinned ring of {token, n_past}
   int h_state_cap_ = 0;
+  long h_state_next_ = 0;
   int* h_tokens_out_ = nullptr;
   int* d_tokens_out_ = nullptr;
   int tokens_out_cap_ = 0;
@@ -124,6 +129,14 @@ class Engine {
   void enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n);
   void build_graphs();
   void destroy_graphs();
+  // batched prefill (prefill.cuh): built on first use
+  struct PrefillState* pf_ = nullptr;
+  bool prefill_on_ = true;       // CTB_NO_PREFILL=1: prompts run through the single-token kernel
+  int prefill_min_ = 4;          // shortest run of consecutive tokens worth a batched launch
+  bool ensure_prefill();
+  void prefill_batch(const int* tokens, const int* pos, const int* n_total, int n, bool last);
+  void decode_one(int token, int pos, int n_total, bool with_logits);
+  void finish_eval(int next_pos, bool hit);
   enum : int { MVK_QKV = 0, MVK_WO = 1, MVK_UP = 2, MVK_DOWN = 3, MVK_OUT = 4 };   // which projection a mat-vec launch is
   bool profiling_ = false;
   bool pdl_ = true;              // programmatic dependent launch between the kernels of a step (CTB_NO_PDL=1 turns it off)

@@ -135,15 +135,22 @@ bool ctransformers_llm_batch_eval(LLM* llm, const int* tokens, const int n_token
   try {
     const int n_ctx = llm->hp.n_ctx;
     const int bs = std::max(1, std::min(n_ctx, batch_size));
+    // LLM::BatchEval (llm.h:40-54): chunks of batch_size tokens, n_past clamped per chunk (llm.h:126).  The chunk a token belongs
+    // to fixes the row length n_total = n_past + N of its attention mat-muls; the engine gets the whole list at once so that
+    // prompt chunks can share batched launches.
+    std::vector<int> pos(n_tokens), nt(n_tokens);
     int past = n_past;
     for (int start = 0; start < n_tokens; start += bs) {
       const int n = std::min(bs, n_tokens - start);
       const int p = std::max(0, std::min(n_ctx - n, past));
-      for (int i = 0; i < n; i++)
+      for (int i = 0; i < n; i++) {
         if (tokens[start + i] < 0 || tokens[start + i] >= llm->hp.n_vocab) throw std::runtime_error("token id out of range");
-      llm->engine->eval(tokens + start, n, p);
+        pos[start + i] = p + i;
+        nt[start + i] = p + n;
+      }
       past += n;
     }
+    llm->engine->eval_list(tokens, pos.data(), nt.data(), n_tokens);
     if (n_tokens > 0) llm->has_logits = true;
     return true;
   } catch (const std::exception& e) {

@@ -42,14 +42,13 @@ __host__ __device__ inline size_t pb_qbuf_bytes(int K) { return (size_t)(K / 256
 
 struct alignas(16) PPhase {
   int kind;
-  int n_tok;              // valid tokens of this launch (<= PB_T)
   MVParams mv;            // QUANT: x, x2, x_mode, norm_*, eps, K;  GEMM: K, nseg, seg[], tables
   int x_ld, x2_ld;        // QUANT: floats between the token rows of x / x2
   int out_ld[MV_MAX_SEG], res_ld[MV_MAX_SEG], res2_ld[MV_MAX_SEG];   // GEMM: floats between token rows
   uint8_t* qbuf;          // QUANT writes, GEMM reads
   AttnParams at;          // KV / ATTN: q, k, v = rows of token 0, strides q_stride / kv_stride; out row stride n_head*hd
   EmbedParams em;         // EMBED: out row stride = K
-  const int* state;       // [PB_T][4]: {token, position, step, n_total} per token
+  const int* state;       // [PB_T][4]: {token, position, step, n_total} per token; state[PB_T*4] = valid tokens of this launch
 };
 
 struct PStepArgs {
@@ -235,7 +234,7 @@ __device__ __forceinline__ void pb_chunk(const uint8_t* slot, int nblk, int b0, 
 // end of a tile: the team's 4 warps publish their accumulators, then its 128 threads finish 16 rows x PB_T tokens:
 // hsum_float_8's tree over the 8 lanes (ggml.c:609-615), the mins tail, the epilogue (store_epilogue of matvec.cuh per token row)
 template <int BARID>
-__device__ __forceinline__ void pb_finish(const PBState& st, float* xch, int type, int lane, int lp, int tid_team, const PPhase& ph, int seg, int row0) {
+__device__ __forceinline__ void pb_finish(const PBState& st, float* xch, int type, int lane, int lp, int tid_team, const PPhase& ph, int n_tok, int seg, int row0) {
   const int g = lane >> 2, t = lane & 3;
   asm volatile("bar.sync %0, %1;" ::"n"(BARID), "n"(128) : "memory");   // the previous tile's readers are done with xch
 #pragma unroll
@@ -259,7 +258,7 @@ __device__ __forceinline__ void pb_finish(const PBState& st, float* xch, int typ
     if (type == GT_Q4_K) v = __fadd_rn(v, __fadd_rn(__fadd_rn(x[8 * L], x[10 * L]), __fadd_rn(x[9 * L], x[11 * L])));
     else if (type == GT_Q5_K) v = __fadd_rn(v, x[8 * L]);
     const int grow = row0 + row;
-    if (grow < sg.w.M && tok < ph.n_tok) {
+    if (grow < sg.w.M && tok < n_tok) {
       if (sg.epi == EPI_ADD) v = __fadd_rn(v, __ldcg(sg.res + (size_t)tok * rld + grow));
       else if (sg.epi == EPI_ADD2) v = __fadd_rn(__fadd_rn(v, __ldcg(sg.res + (size_t)tok * rld + grow)), __ldcg(sg.res2 + (size_t)tok * r2ld + grow));
       else if (sg.epi == EPI_GELU) v = table_f16(ph.mv.gelu_tab, v);
@@ -309,7 +308,7 @@ __device__ __forceinline__ void pb_producer(const PStepArgs& args, uint8_t* ring
   }
 }
 
-__device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, uint8_t* ring, float* xch_all, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t& seq) {
+__device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8_t* ring, float* xch_all, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t& seq) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = warp >> 2, lp = warp & 3;
   float* xch = xch_all + (size_t)team * (PB_XCH / 4);
@@ -346,17 +345,17 @@ __device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, uint8_t* ring, f
       seq += (uint32_t)__popc(mask);
     }
     if (team < ntw) {
-      if (team == 0) pb_finish<2>(st, xch, my_type, lane, lp, threadIdx.x & 127, ph, my_seg, my_til * ST_ROWS);
-      else pb_finish<3>(st, xch, my_type, lane, lp, threadIdx.x & 127, ph, my_seg, my_til * ST_ROWS);
+      if (team == 0) pb_finish<2>(st, xch, my_type, lane, lp, threadIdx.x & 127, ph, n_tok, my_seg, my_til * ST_ROWS);
+      else pb_finish<3>(st, xch, my_type, lane, lp, threadIdx.x & 127, ph, n_tok, my_seg, my_til * ST_ROWS);
     }
   }
 }
 
 // RoPE of K + fp16 store of K and V of every valid token (the KV half of k_rope_kv, attention.cuh)
-__device__ __forceinline__ void pb_kv_phase(const PPhase& ph) {
+__device__ __forceinline__ void pb_kv_phase(const PPhase& ph, int n_tok) {
   const AttnParams& a = ph.at;
   const int half = a.hd / 2, per_tok = a.n_kv * half;
-  const int total = ph.n_tok * per_tok, cp = kv_ctx_pad(a.n_ctx);
+  const int total = n_tok * per_tok, cp = kv_ctx_pad(a.n_ctx);
   for (int idx = blockIdx.x * PB_NT + threadIdx.x; idx < total; idx += gridDim.x * PB_NT) {
     const int tok = idx / per_tok, r = idx % per_tok, kh = r / half, i = r % half;
     const int pos = ph.state[tok * 4 + 1];
@@ -411,10 +410,11 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
       while (ld_acquire_u32(args.sync) < target) { }
     }
     bar_sync<PB_BAR, PB_NT>();
+    const int n_tok = min(PB_T, ph.state[PB_T * 4]);
     if (ph.kind == PP_GEMM) {
-      pb_gemm_phase(ph, ring, (float*)work, full_bar, empty_bar, (uint32_t)args.n_slots, seq);
+      pb_gemm_phase(ph, n_tok, ring, (float*)work, full_bar, empty_bar, (uint32_t)args.n_slots, seq);
     } else if (ph.kind == PP_QUANT) {
-      for (int tok = blockIdx.x; tok < ph.n_tok; tok += G) {
+      for (int tok = blockIdx.x; tok < n_tok; tok += G) {
         MVParams q = ph.mv;
         q.x = ph.mv.x + (size_t)tok * ph.x_ld;
         if (q.x2) q.x2 = ph.mv.x2 + (size_t)tok * ph.x2_ld;
@@ -424,9 +424,9 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
         pb_quant_store<PB_NT, PB_BAR>(work, q.K, tok, ph.qbuf);
       }
     } else if (ph.kind == PP_KV) {
-      pb_kv_phase(ph);
+      pb_kv_phase(ph, n_tok);
     } else if (ph.kind == PP_ATTN) {
-      const int n_cg = ph.at.hd / ATTN_CH, per_tok = ph.at.n_head * n_cg, n_tasks = ph.n_tok * per_tok;
+      const int n_cg = ph.at.hd / ATTN_CH, per_tok = ph.at.n_head * n_cg, n_tasks = n_tok * per_tok;
       bool first = true;
       for (int task = blockIdx.x; task < n_tasks; task += G) {
         if (!first) bar_sync<PB_BAR, PB_NT>();
@@ -435,7 +435,7 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
         attn_body<PB_NT, PB_BAR, false>(ph.at, work, r / n_cg, tok, r % n_cg, ph.state + tok * 4);
       }
     } else if (ph.kind == PP_EMBED) {
-      for (int tok = blockIdx.x; tok < ph.n_tok; tok += G) {
+      for (int tok = blockIdx.x; tok < n_tok; tok += G) {
         const int id = ph.state[tok * 4];
         const uint8_t* row = ph.em.table + (size_t)min(max(id, 0), ph.em.n_vocab - 1) * ph.em.row_bytes;
         float* o = ph.em.out + (size_t)tok * ph.em.K;

@@ -199,3 +199,35 @@ def test_bench_model_against_live_reference(workload):
     same_bits(ours[1], theirs[1])
     assert ours[2] == theirs[2]
     same_bits(ours[3], theirs[3])
+
+
+# ---- batched prefill (csrc/prefill.cuh): prompts longer than a few tokens go through the dense int8 tensor-core kernel
+@pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not present")
+@pytest.mark.parametrize("name,bs", [("llama_wide_q4km", 512), ("llama_wide_q4km", 64), ("llama_gqa_q5km", 5), ("falcon_tiny_q5km", 512)])
+def test_prefill_against_live_reference(name, bs, model_dir):
+    """A prompt of 70 tokens (3 batched launches: 32 + 32 + 6) at batch_size 5 / 64 / 512: logits and hidden state after the
+    prompt and the greedy continuation must be the reference's, bit for bit."""
+    path, _ = modelcases.build(name, model_dir)
+    arch, shape, _, _ = modelcases.CASES[name]
+    rng = np.random.default_rng(9)
+    prompt = rng.integers(259 if arch == "llama" else 0, shape.n_vocab, 70).tolist()
+    if arch == "llama":
+        prompt[0] = 1
+    ours = modelcases.run_greedy(load(path, 96), prompt, 6, batch_size=bs)
+    theirs = modelcases.run_greedy(load(path, 96, lib=str(refs.REF_SO), threads=4), prompt, 6, batch_size=bs)
+    same_bits(ours[0], theirs[0])
+    same_bits(ours[1], theirs[1])
+    assert ours[2] == theirs[2]
+    same_bits(ours[3], theirs[3])
+
+
+def test_prefill_equals_single_token_path(model_dir, monkeypatch):
+    """The batched kernel and the single-token kernel are two implementations of the same arithmetic: identical bits."""
+    path, _ = modelcases.build("llama_wide_q4km", model_dir)
+    prompt = modelcases.prompt_for("llama_wide_q4km")
+    a = modelcases.run_greedy(load(path, 96), prompt, 4, batch_size=16)
+    monkeypatch.setenv("CTB_NO_PREFILL", "1")
+    b = modelcases.run_greedy(load(path, 96), prompt, 4, batch_size=16)
+    same_bits(a[0], b[0])
+    same_bits(a[1], b[1])
+    assert a[2] == b[2]
