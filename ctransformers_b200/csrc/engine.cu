@@ -11,6 +11,7 @@
 #include "matvec.cuh"
 #include "prefill.cuh"
 #include "repack.cuh"
+#include "sample_gpu.cuh"
 #include "stream.cuh"
 #include "tables.hpp"
 
@@ -63,7 +64,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += 3 * align_up(65536 * 2, 256);
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
-  total += 4 * (2 * (size_t)hp.n_embd + qkv + 3 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + (size_t)hp.n_vocab) + 64 * 256;
+  total += 4 * (2 * (size_t)hp.n_embd + qkv + 4 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + 2 * (size_t)hp.n_vocab) + 64 * 256 + 8192;
   total += ((size_t)hp.n_layer * 8 + 8) * sizeof(Phase) * 2 + 4096;   // the step programs
   total += 1 << 20;
   return total;
@@ -331,6 +332,8 @@ void Engine::init(const GGUFFile& g) {
   ffn2_ = (float*)alloc((size_t)hp_.n_ff * 4);
   d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
   d_embd_ = (float*)alloc(hp_.n_embd * 4);
+  d_logits_keep_ = (float*)alloc((size_t)hp_.n_vocab * 4);
+  d_embd_keep_ = (float*)alloc(hp_.n_embd * 4);
   d_sync_ = (unsigned*)alloc(64);
   CTB_CUDA(cudaMemset(d_state_, 0, 64));
   CTB_CUDA(cudaMemset(d_sync_, 0, 64));
@@ -366,6 +369,8 @@ void Engine::release() {
   if (d_tokens_out_) cudaFree(d_tokens_out_);
   if (arena_) cudaFree(arena_);
   if (h_spec_tok_) cudaFreeHost(h_spec_tok_);
+  if (h_sample_) cudaFreeHost(h_sample_);
+  h_sample_ = nullptr;
   if (ev_pick_) cudaEventDestroy(ev_pick_);
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -758,9 +763,55 @@ void Engine::decode_one(int token, int pos, int n_total, bool with_logits) {
   CTB_CUDA(cudaGraphLaunch(with_logits ? graph_full_ : graph_nolog_, stream_));
 }
 
+void Engine::host_views() {
+  eager_ = true;
+  if (host_fresh_) return;
+  CTB_CUDA(cudaSetDevice(device_));
+  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_keep_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_keep_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  host_fresh_ = true;
+}
+
+std::vector<float> Engine::logits_copy() {
+  std::vector<float> v((size_t)hp_.n_vocab);
+  if (host_fresh_) { memcpy(v.data(), h_logits_, v.size() * 4); return v; }
+  CTB_CUDA(cudaSetDevice(device_));
+  CTB_CUDA(cudaMemcpyAsync(v.data(), d_logits_keep_, v.size() * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  return v;
+}
+
+int Engine::topk_candidates(const int* last, int n_last, float penalty, int k, int* ids, float* logits) {
+  if (n_last > SG_MAX_LAST || k < 1 || k > SG_MAX_OUT / 2) return -1;
+  CTB_CUDA(cudaSetDevice(device_));
+  if (!d_sample_) {
+    d_sample_ = (SampleGpuOut*)alloc(sizeof(SampleGpuOut));
+    d_last_ = (int*)alloc(SG_MAX_LAST * 4 + 16);
+    CTB_CUDA(cudaMallocHost(&h_sample_, sizeof(SampleGpuOut) + SG_MAX_LAST * 4));
+  }
+  int* h_last = (int*)(h_sample_ + 1);
+  for (int i = 0; i < n_last; i++) h_last[i] = last[i];
+  if (n_last > 0) CTB_CUDA(cudaMemcpyAsync(d_last_, h_last, (size_t)n_last * 4, cudaMemcpyHostToDevice, stream_));
+  k_sample_topk<<<1, SG_THREADS, 0, stream_>>>(d_logits_keep_, hp_.n_vocab, d_last_, n_last, penalty, std::min(k, hp_.n_vocab), d_sample_);
+  CTB_CUDA(cudaGetLastError());
+  CTB_CUDA(cudaMemcpyAsync(h_sample_, d_sample_, sizeof(SampleGpuOut), cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  const int n = h_sample_->count;
+  if (n < 0 || n > SG_MAX_OUT) return -1;
+  for (int i = 0; i < n; i++) { ids[i] = h_sample_->id[i]; logits[i] = h_sample_->logit[i]; }
+  return n;
+}
+
 void Engine::finish_eval(int next_pos, bool hit) {
-  CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
-  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  // the look-ahead step (after_eval) overwrites d_logits_ / d_embd_: keep this eval's results where a late request finds them
+  CTB_CUDA(cudaMemcpyAsync(d_logits_keep_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToDevice, stream_));
+  CTB_CUDA(cudaMemcpyAsync(d_embd_keep_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
+  if (eager_) {
+    CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+    CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  }
+  host_fresh_ = eager_;
   CTB_CUDA(cudaEventRecord(ev1_, stream_));
   after_eval(next_pos);
   CTB_CUDA(cudaEventSynchronize(ev1_));
@@ -952,7 +1003,11 @@ double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_
   CTB_CUDA(cudaEventRecord(ev1_, stream_));
   CTB_CUDA(cudaMemcpyAsync(h_tokens_out_, d_tokens_out_, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(d_logits_keep_, d_logits_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToDevice, stream_));
+  CTB_CUDA(cudaMemcpyAsync(d_embd_keep_, d_embd_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToDevice, stream_));
   CTB_CUDA(cudaStreamSynchronize(stream_));
+  host_fresh_ = true;
   memcpy(out_tokens, h_tokens_out_, (size_t)n_steps * 4);
   float ms = 0;
   cudaEventElapsedTime(&ms, ev0_, ev1_);

@@ -62,8 +62,16 @@ class Engine {
   double time_matvec_only(int reps, long* launches, unsigned mask = 0);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
 
-  float* logits() { return h_logits_; }
-  float* embeddings() { return h_embd_; }
+  // Host views of the last token's logits / hidden state (the reference hands out ctx->logits.data(), mutable by the caller,
+  // llama.cc:47-51).  Until a caller asks for one, nothing is copied per eval (lazy); from the first request on every eval
+  // refreshes them, because the caller may keep the pointer.
+  float* logits() { host_views(); return h_logits_; }
+  float* embeddings() { host_views(); return h_embd_; }
+  bool lazy_logits() const { return !eager_; }
+  std::vector<float> logits_copy();   // this eval's logits without switching the engine to eager host views
+  // Device half of the sampler (sample_gpu.cuh): candidates >= the k-th largest penalised logit.  Returns their count, or -1
+  // when the device path does not apply (window too long, k too large).
+  int topk_candidates(const int* last, int n_last, float penalty, int k, int* ids, float* logits);
   const HParams& hparams() const { return hp_; }
   EvalStats stats;
   void set_stream(cudaStream_t s);   // run on a caller-owned stream (bench: torch's current stream)
@@ -90,7 +98,7 @@ class Engine {
   uint16_t *kc_ = nullptr, *vc_ = nullptr;
   // workspace
   int* d_state_ = nullptr;     // {token, n_past}
-  float *xa_ = nullptr, *xb_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *attn_o_ = nullptr, *ffn_ = nullptr, *ffn2_ = nullptr, *d_logits_ = nullptr, *d_embd_ = nullptr;
+  float *xa_ = nullptr, *xb_ = nullptr, *qkv_ = nullptr, *attn_ = nullptr, *attn_o_ = nullptr, *ffn_ = nullptr, *ffn2_ = nullptr, *d_logits_ = nullptr, *d_embd_ = nullptr, *d_logits_keep_ = nullptr, *d_embd_keep_ = nullptr;
   // host (pinned) results
   float *h_logits_ = nullptr, *h_embd_ = nullptr;
   int* h_state_ = nullptr;     // pinned ring of {token, n_past}
@@ -129,6 +137,12 @@ class Engine {
   void enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n);
   void build_graphs();
   void destroy_graphs();
+  bool eager_ = false;           // host logits / embeddings are refreshed by every eval
+  bool host_fresh_ = true;
+  void host_views();
+  struct SampleGpuOut* d_sample_ = nullptr;
+  struct SampleGpuOut* h_sample_ = nullptr;
+  int* d_last_ = nullptr;
   // batched prefill (prefill.cuh): built on first use
   struct PrefillState* pf_ = nullptr;
   bool prefill_on_ = true;       // CTB_NO_PREFILL=1: prompts run through the single-token kernel

@@ -35,6 +35,7 @@ struct LLM {
   std::string piece_buf;
   std::mt19937 rng;
   bool has_logits = false;
+  long gpu_samples = 0;   // sample() calls answered by the device-side penalty + top-k
 };
 
 static bool file_is_gguf(const char* path) {
@@ -169,6 +170,20 @@ int ctransformers_llm_sample(LLM* llm, const int* last_tokens, const int n_last,
   try {
     if (seed < 0) seed = (int)time(nullptr);
     llm->rng.seed((unsigned)seed);
+    if (llm->engine->lazy_logits()) {
+      // nobody holds a host view of the logits: penalty + top-k run on the device, only the candidates come back
+      int ids[256];
+      float lg[256];
+      const int count = llm->engine->topk_candidates(last_tokens, n_last, repetition_penalty, top_k, ids, lg);
+      std::vector<Candidate> c;
+      if (count > 0 && device_candidates_usable(ids, lg, count, top_k, llm->hp.n_vocab, c)) {
+        llm->gpu_samples++;
+        return sample_candidates(c, top_k, top_p, temperature, llm->rng);
+      }
+      // ambiguous cut (equal logits): the reference's own sort over all candidates decides — host path on a private copy
+      std::vector<float> all = llm->engine->logits_copy();
+      return sample_token(all.data(), llm->hp.n_vocab, last_tokens, n_last, top_k, top_p, temperature, repetition_penalty, llm->rng);
+    }
     return sample_token(llm->engine->logits(), llm->hp.n_vocab, last_tokens, n_last, top_k, top_p, temperature, repetition_penalty, llm->rng);
   } catch (...) { return llm->vocab.eos; }
 }
@@ -182,6 +197,7 @@ double ctb_llm_last_eval_ms(LLM* llm) { return llm->engine->stats.last_eval_ms; 
 long ctb_llm_launches_per_token(LLM* llm) { return llm->engine->stats.launches; }
 long ctb_llm_speculative_hits(LLM* llm) { return llm->engine->stats.spec_hits; }
 unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm) { return (unsigned long long)llm->engine->stats.weight_bytes_per_token; }
+long ctb_llm_device_samples(LLM* llm) { return llm->gpu_samples; }
 double ctb_llm_load_ms(LLM* llm) { return llm->engine->stats.load_ms; }
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream) { llm->engine->set_stream((cudaStream_t)cuda_stream); }
 

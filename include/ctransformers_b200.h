@@ -64,6 +64,10 @@ long ctb_llm_launches_per_token(LLM* llm);          /* kernels in one decode ste
  * CTB_NO_SPEC=1 in the environment turns that look-ahead off. */
 long ctb_llm_speculative_hits(LLM* llm);
 unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm); /* algorithmic weight bytes one decode step reads */
+/* sample() calls answered by the device-side repetition penalty + top-k (csrc/sample_gpu.cuh): used while no caller holds a
+ * host view of the logits (logits_data / embeddings_data never called); otherwise, or when equal logits make the top-k cut
+ * ambiguous, the host sampler runs on the full logits exactly as the reference does. */
+long ctb_llm_device_samples(LLM* llm);
 /* wall-clock milliseconds the weight upload took (mmap -> pinned staging -> H2D -> repack, pipelined; engine.cu Uploader) */
 double ctb_llm_load_ms(LLM* llm);
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream);        /* run on a caller-owned cudaStream_t */

@@ -231,3 +231,34 @@ def test_prefill_equals_single_token_path(model_dir, monkeypatch):
     same_bits(a[0], b[0])
     same_bits(a[1], b[1])
     assert a[2] == b[2]
+
+
+def test_device_sampler_draws_the_reference_tokens(model_dir):
+    """sample() before anybody has asked for llm.logits runs repetition penalty + top-k on the device (csrc/sample_gpu.cuh) and
+    the rest on the host; after llm.logits has been read the whole chain runs on the host logits like the reference's.  Same
+    seeds, same tokens — and the host chain is the one pinned against the reference in test_host_logic.py."""
+    path, ctx = modelcases.build("llama_tiny_q4km", model_dir)
+    llm = load(path, ctx)
+    prompt = modelcases.prompt_for("llama_tiny_q4km")
+    llm.eval(prompt)
+    last = prompt[-20:] + [7, 7, 300]
+    cases = [(40, 0.95, 0.8, 1.1, s) for s in range(6)] + [(1, 1.0, 1.0, 1.0, 0), (5, 0.5, 1.3, 1.3, 3), (100, 0.9, 0.7, 1.0, 4), (64, 1.0, 2.0, 1.5, 5)]
+
+    def draw(k, p, t, rp, seed):
+        arr = (C.c_int * len(last))(*last)
+        return llm.ctransformers_llm_sample(arr, len(last), k, p, t, rp, seed)
+
+    before = llm.ctb_llm_device_samples()
+    dev = [draw(*c) for c in cases]
+    assert llm.ctb_llm_device_samples() - before >= len(cases) - 1       # (equal logits may send a case to the host path)
+    _ = llm.logits[0]                                                      # a host view exists from here on
+    mid = llm.ctb_llm_device_samples()
+    host = [draw(*c) for c in cases]
+    assert llm.ctb_llm_device_samples() == mid
+    assert dev == host
+    # and the lazily fetched logits are the eval's logits: a fresh engine that copies eagerly agrees
+    llm2 = load(path, ctx)
+    _ = llm2.logits
+    llm2.eval(prompt)
+    same_bits(np.array(llm.logits, np.float32), np.array(llm2.logits, np.float32))
+    same_bits(np.array(llm.embeddings, np.float32), np.array(llm2.embeddings, np.float32))
