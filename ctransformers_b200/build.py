@@ -39,36 +39,40 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link libctransformers.so.  Returns the library path."""
+def build(force=False, verbose=False, variant=None, defines=()):
+    """Compile every CUDA source for sm_100a and link libctransformers.so.  Returns the library path.
+    variant + defines: an A/B build (tools/ab.py) with extra -D flags, written to lib/libctransformers_<variant>.so."""
     OUT_DIR.mkdir(exist_ok=True)
-    OBJ_DIR.mkdir(parents=True, exist_ok=True)
-    stamp = OBJ_DIR / "digest"
-    dig = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == dig:
-        return LIB
+    obj_dir = OBJ_DIR if not variant else OBJ_DIR.parent / f"obj_{variant}"
+    lib = LIB if not variant else OUT_DIR / f"libctransformers_{variant}.so"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    stamp = obj_dir / "digest"
+    dig = _digest() + "|" + " ".join(defines)
+    if not force and lib.exists() and stamp.exists() and stamp.read_text() == dig:
+        return lib
     exe = nvcc()
 
     def compile_one(src):
-        obj = OBJ_DIR / (src + ".o")
-        cmd = [exe, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        obj = obj_dir / (src + ".o")
+        cmd = [exe, *NVCC_FLAGS, *defines, "-c", str(CSRC / src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
-        (OBJ_DIR / (src + ".ptxas.log")).write_text(r.stderr)
+        (obj_dir / (src + ".ptxas.log")).write_text(r.stderr)
         if verbose:
             print(r.stderr, file=sys.stderr)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [exe, "-shared", "-o", str(LIB), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    cmd = [exe, "-shared", "-o", str(lib), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     stamp.write_text(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")), None)
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var, defines=[a for a in sys.argv[1:] if a.startswith("-D")]))

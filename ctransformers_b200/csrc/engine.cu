@@ -684,6 +684,35 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   return (double)ms / reps;
 }
 
+// One fused decode step with the step kernel stamping %globaltimer per phase and CTA (4 stamps: barrier passed, input staged,
+// first weight item ready, phase done).  out: n_phases x {kind, mvk} then n_phases x n_cta x 4 stamps; returns n_phases or -(words needed).
+long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
+  CTB_CUDA(cudaSetDevice(device_));
+  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  const int n = n_body_ + 1;
+  for (int i = 0; i < n; i++)
+    if (ops_[i].ph.kind == PH_MATVEC && !ops_[i].stream) return 0;
+  const long need = 2L * n + 4L * n * step_grid_;
+  if (need > cap_words) return -need;
+  unsigned long long* buf = nullptr;
+  CTB_CUDA(cudaMalloc(&buf, (size_t)n * step_grid_ * 32));
+  CTB_CUDA(cudaMemset(buf, 0, (size_t)n * step_grid_ * 32));
+  StepLaunch L;
+  L.grid = step_grid_; L.n_slots = step_slots_; L.smem = step_smem_;
+  if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
+  for (int rep = 0; rep < 3; rep++) {   // the last (warm) run is the one read back
+    h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
+    CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
+    CTB_CUDA(launch_step(L, stream_, d_prog_, n, d_sync_, false, buf));
+    CTB_CUDA(cudaStreamSynchronize(stream_));
+  }
+  for (int i = 0; i < n; i++) { out[2 * i] = (unsigned long long)ops_[i].ph.kind; out[2 * i + 1] = (unsigned long long)ops_[i].mvk; }
+  const cudaError_t e = cudaMemcpy(out + 2 * n, buf, (size_t)n * step_grid_ * 32, cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  CTB_CUDA(e);
+  return n;
+}
+
 void Engine::destroy_graphs() {
   if (graph_full_) cudaGraphExecDestroy(graph_full_);
   if (graph_nolog_) cudaGraphExecDestroy(graph_nolog_);

@@ -61,6 +61,7 @@ class Engine {
   // per-class device time.  kinds: 0 mat-vec, 1 attention, 2 rope+kv store, 3 other.  Returns kernel count.
   double time_matvec_only(int reps, long* launches, unsigned mask = 0);
   int profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]);
+  long trace_step(int token, int n_past, unsigned long long* out, long cap_words);
 
   // Host views of the last token's logits / hidden state (the reference hands out ctx->logits.data(), mutable by the caller,
   // llama.cc:47-51).  Until a caller asks for one, nothing is copied per eval (lazy); from the first request on every eval

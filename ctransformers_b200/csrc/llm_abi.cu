@@ -221,6 +221,15 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
   }
 }
 
+long ctb_llm_trace_step(LLM* llm, int token, int n_past, unsigned long long* out, long cap_words) {
+  try {
+    return llm->engine->trace_step(token, n_past, out, cap_words);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "ctransformers-b200: trace_step failed: %s\n", e.what());
+    return 0;
+  }
+}
+
 double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches) { return ctb_llm_time_matvec_kinds(llm, reps, launches, 0); }
 
 double ctb_llm_time_matvec_kinds(LLM* llm, int reps, long* launches, unsigned kind_mask) {

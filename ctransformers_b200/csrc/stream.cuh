@@ -481,6 +481,7 @@ struct StepArgs {
   int n_phases;
   int n_slots;
   unsigned* sync;   // [0] grid-barrier arrivals, [1] finished CTAs (the last one resets both)
+  unsigned long long* trace;   // optional: per phase and CTA 4 globaltimer stamps {barrier passed, input staged, first item ready, phase done}
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -547,11 +548,13 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
 
 // Consumer side of one mat-vec phase.  `seq` is the running item number (identical in every warp and in the producer).
 __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& np, uint8_t* ring, uint8_t* act_smem, double* red, uint64_t* full_bar, uint64_t* empty_bar,
-                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq) {
+                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, unsigned long long* tr) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0);
   const StAct a = st_act_extras<ST_NT, ST_BAR>(act_smem, p.K, ph.q6 != 0);
+  if (tr && threadIdx.x == 0) tr[1] = globaltimer_ns();
+  bool first_item = tr != nullptr && threadIdx.x == 0;
   TileSpace ts;
   ts.init(p);
   const int T0 = ts.boundary(blockIdx.x, gridDim.x), T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
@@ -581,6 +584,7 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
         const MVSeg& sg = p.seg[seg];
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
         mbar_wait(&full_bar[slot], (n / S) & 1u);
+        if (first_item) { tr[2] = globaltimer_ns(); first_item = false; }
         volatile float* mail = mailbox[j];
         volatile int* flag = flags + j;
         const bool last = kc == nch - 1;
@@ -666,8 +670,10 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
       while (ld_acquire_u32(args.sync) < target) { }
     }
     bar_sync<ST_BAR, ST_NT>();
+    unsigned long long* const tr = args.trace ? args.trace + ((size_t)ip * G + blockIdx.x) * 4 : nullptr;
+    if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
     if (ph.kind == PH_MATVEC) {
-      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq);
+      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq, tr);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
       for (int task = blockIdx.x; task < n_tasks; task += G) {
@@ -682,6 +688,10 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
       }
     } else if (ph.kind == PH_PICK) {
       if (blockIdx.x == 0) st_pick_phase(ph.pk, pick_v, pick_i);
+    }
+    if (tr) {
+      bar_sync<ST_BAR, ST_NT>();
+      if (threadIdx.x == 0) tr[3] = globaltimer_ns();
     }
   }
   bar_sync<ST_BAR, ST_NT>();
@@ -741,9 +751,10 @@ static inline size_t step_max_dyn_smem() {
 }
 static inline cudaError_t step_set_smem_limit(size_t bytes) { return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
-static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, int n_phases, unsigned* d_sync, bool pdl = false) {
+static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, int n_phases, unsigned* d_sync, bool pdl = false,
+                                      unsigned long long* trace = nullptr) {
   StepArgs a;
-  a.prog = d_prog; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync;
+  a.prog = d_prog; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync; a.trace = trace;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
   cudaLaunchAttribute at[1];

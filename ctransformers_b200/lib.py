@@ -62,6 +62,7 @@ EXTRA_PROTOTYPES = {
     "ctb_llm_launches_per_token": (C.c_long, [_P]),
     "ctb_llm_speculative_hits": (C.c_long, [_P]),
     "ctb_llm_weight_bytes_per_token": (C.c_ulonglong, [_P]),
+    "ctb_llm_trace_step": (C.c_long, [_P, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.c_long]),
     "ctb_llm_load_ms": (C.c_double, [_P]),
     "ctb_llm_device_samples": (C.c_long, [_P]),
     "ctb_llm_set_stream": (None, [_P, C.c_void_p]),

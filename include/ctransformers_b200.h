@@ -81,6 +81,10 @@ int ctb_llm_profile_step(LLM* llm, int token, int n_past, double* ms_by_kind, in
 /* The mat-vec phases of one decode step alone (same kernel, parameters and order; attention, embedding and pick left
  * out), replayed reps times as a CUDA graph between two CUDA events: returns milliseconds per step, < 0 on error;
  * *launches = mat-vec phases per step.  KV cache and logits are not meaningful afterwards. */
+/* One fused decode step whose step-kernel CTAs stamp %globaltimer (ns) per phase: out = n_phases x {phase kind, projection},
+ * then n_phases x n_cta x {barrier passed, input staged, first weight item in shared memory, phase done}.  Returns the number
+ * of phases, 0 if the model does not run fused, or -(words needed). */
+long ctb_llm_trace_step(LLM* llm, int token, int n_past, unsigned long long* out, long cap_words);
 double ctb_llm_time_matvec_only(LLM* llm, int reps, long* launches);
 /* Same, restricted to the launches whose kind bit is set in kind_mask (bit 0 QKV, 1 attention output, 2 FFN gate+up,
  * 3 FFN down, 4 output head; 0 = all): per-projection timing under in-graph launch conditions. */
