@@ -75,9 +75,11 @@ static __global__ void k_embed(const uint8_t* table, int type, size_t row_bytes,
 // KV cache layouts (ours; the reference keeps K [n_ctx][n_embd_gqa] and V transposed [n_embd_gqa][n_ctx], llama.cpp:2323-2335).
 // Both are permuted so that the GPU lane that plays lane L of the reference's 4x8-lane f16 dot (ggml_vec_dot_f16,
 // ggml.c:2392-2426: lane L accumulates elements 32i+L in order i) finds ITS elements contiguous:
-//   K: [n_ctx][n_kv][hd]        element e of a head row is stored at (e & 31) * (hd/32) + (e >> 5)
+//   K: [n_kv][n_ctx][hd]        head-major (a head's rows of positions 0..T-1 are one contiguous run: one bulk copy brings a
+//                               stretch of them into shared memory); element e of a row is stored at (e & 31) * (hd/32) + (e >> 5)
 //   V: [n_kv][hd][ctx_pad]      (channel-major like the reference) position t at (t & ~255) + (t & 31) * 8 + ((t >> 5) & 7)
 __host__ __device__ inline int kv_ctx_pad(int n_ctx) { return (n_ctx + 255) & ~255; }
+__host__ __device__ inline size_t k_row(int kv_head, int pos, int n_ctx, int hd) { return ((size_t)kv_head * n_ctx + pos) * hd; }   // element offset of a K row
 __host__ __device__ inline int k_perm(int e, int hd) { return (e & 31) * (hd >> 5) + (e >> 5); }
 __host__ __device__ inline int v_perm(int t) { return (t & ~255) + (t & 31) * 8 + ((t >> 5) & 7); }
 
@@ -125,7 +127,7 @@ static __global__ void k_rope_kv(const RopeKVParams p) {
     const float* vsrc = p.v + (size_t)n * p.kv_stride + (size_t)kh * p.hd;
     float o0, o1;
     rope_pair(ksrc[i0], ksrc[i1], cs, p.neox, o0, o1);
-    uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kh) * p.hd;
+    uint16_t* kd = p.kc + k_row(kh, pos, p.n_ctx, p.hd);
     kd[k_perm(i0, p.hd)] = f2h(o0);
     kd[k_perm(i1, p.hd)] = f2h(o1);
     const int cp = kv_ctx_pad(p.n_ctx);
@@ -232,13 +234,13 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int t = min(warp * 8 + i, T - 1);
-      kpre[i] = (t == pos) ? make_uint2(0, 0) : *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
+      kpre[i] = (t == pos) ? make_uint2(0, 0) : *(const uint2*)(p.kc + k_row(kvh, t, p.n_ctx, hd) + lane * 4);
     }
   } else if (per == 2) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
       const int t = min(warp * 8 + i, T - 1);
-      kpre[i] = make_uint2((t == pos) ? 0u : *(const uint32_t*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 2), 0u);
+      kpre[i] = make_uint2((t == pos) ? 0u : *(const uint32_t*)(p.kc + k_row(kvh, t, p.n_ctx, hd) + lane * 2), 0u);
     }
   }
   if (threadIdx.x < hd / 2) cs_pre = p.rope[(size_t)pos * (hd / 2) + threadIdx.x];
@@ -248,7 +250,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
     const float* qv = p.q + (size_t)n * p.q_stride + (size_t)h * hd;
     const float* kv = p.k + (size_t)n * p.kv_stride + (size_t)kvh * hd;
     const float* vv = p.v + (size_t)n * p.kv_stride + (size_t)kvh * hd;
-    uint16_t* kd = p.kc + ((size_t)pos * p.n_kv + kvh) * hd;
+    uint16_t* kd = p.kc + k_row(kvh, pos, p.n_ctx, hd);
     for (int i = threadIdx.x; i < hd / 2; i += NT) {
       const float2 cs = i == (int)threadIdx.x ? cs_pre : p.rope[(size_t)pos * (hd / 2) + i];
       const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
@@ -279,7 +281,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
         const int t = min(t0 + i, T - 1);
         if (t == pos) kk[i] = *(const uint2*)(k16 + lane * 4);
         else if (t0 == warp * 8) kk[i] = kpre[i];
-        else kk[i] = *(const uint2*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 4);
+        else kk[i] = *(const uint2*)(p.kc + k_row(kvh, t, p.n_ctx, hd) + lane * 4);
       }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -303,7 +305,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
         const int t = min(t0 + i, T - 1);
         if (t == pos) kk[i] = *(const uint32_t*)(k16 + lane * 2);
         else if (t0 == warp * 8) kk[i] = kpre[i].x;
-        else kk[i] = *(const uint32_t*)(p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * 2);
+        else kk[i] = *(const uint32_t*)(p.kc + k_row(kvh, t, p.n_ctx, hd) + lane * 2);
       }
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -316,7 +318,7 @@ __device__ __forceinline__ void attn_body(const AttnParams& p, uint8_t* smem, co
     }
   } else {
     for (int t = warp; t < T; t += NW) {
-      const uint16_t* kr = (t == pos) ? (k16 + lane * per) : (p.kc + ((size_t)t * p.n_kv + kvh) * hd + lane * per);
+      const uint16_t* kr = (t == pos) ? (k16 + lane * per) : (p.kc + k_row(kvh, t, p.n_ctx, hd) + lane * per);
       float s = 0.f;
       for (int i = 0; i < per; i++) s = __fmaf_rn(h2f(kr[i]), h2f(q16[lane * per + i]), s);
       s = attn_reduce_f32x8(s);

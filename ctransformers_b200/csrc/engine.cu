@@ -65,7 +65,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
   total += 4 * (2 * (size_t)hp.n_embd + qkv + 4 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + 2 * (size_t)hp.n_vocab) + 64 * 256 + 8192;
-  total += ((size_t)hp.n_layer * 8 + 8) * sizeof(Phase) * 2 + 4096;   // the step programs
+  total += ((size_t)hp.n_layer * 8 + 8) * (sizeof(Phase) * 2 + 1024) + 4096;   // the step programs and their per-CTA tile ranges
   total += 1 << 20;
   return total;
 }
@@ -526,6 +526,14 @@ void Engine::build_ops() {
     op.ph.kind = PH_PICK;
     op.ph.pk.logits = d_logits_; op.ph.pk.state = d_state_; op.ph.pk.out_tokens = nullptr; op.ph.pk.n = hp_.n_vocab;   // out_tokens: set in build_graphs
     ops_.push_back(op);
+  }
+  // ---- per-CTA tile ranges of every step-kernel mat-vec, computed once
+  for (StepOp& op : ops_) {
+    if (op.ph.kind != PH_MATVEC || !op.stream) continue;
+    const std::vector<int> b = step_bounds(op.ph.mv, sm_count_);
+    int* d = (int*)alloc(b.size() * 4);
+    CTB_CUDA(cudaMemcpy(d, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    op.ph.bounds = d;
   }
   // ---- the step kernel's shared-memory shape: ring slots fill what the largest activation image leaves
   bool any_stream = false;

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -106,10 +107,18 @@ int sm_count() {
 }
 
 // a program of phases through the persistent step kernel, exactly as the engine launches it
-void run_phases(const std::vector<Phase>& phs) {
+void run_phases(std::vector<Phase> phs) {
   static unsigned* d_sync = nullptr;
   if (!d_sync) { OPS_CUDA(cudaMalloc((void**)&d_sync, 64)); OPS_CUDA(cudaMemset(d_sync, 0, 64)); }
   const StepLaunch L = step_launch_shape(phs.data(), (int)phs.size(), sm_count(), step_max_dyn_smem());
+  std::vector<std::unique_ptr<DevBuf>> bounds;
+  for (Phase& ph : phs) {
+    if (ph.kind != PH_MATVEC) continue;
+    const std::vector<int> b = step_bounds(ph.mv, L.grid);
+    bounds.emplace_back(new DevBuf(b.size() * 4));
+    OPS_CUDA(cudaMemcpy(bounds.back()->p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    ph.bounds = bounds.back()->as<int>();
+  }
   if (L.n_slots < 2) throw std::runtime_error("rows too long for the step kernel's shared memory");
   OPS_CUDA(step_set_smem_limit(L.smem));
   DevBuf dprog((phs.size() + 1) * sizeof(Phase));
@@ -291,7 +300,7 @@ int ctb_attention(const float* q, const uint16_t* kcache, const uint16_t* vcache
     for (int t = 0; t < T; t++)
       for (int kh = 0; kh < n_kv; kh++)
         for (int e = 0; e < head_dim; e++)
-          kp[((size_t)t * n_kv + kh) * head_dim + k_perm(e, head_dim)] = kcache[((size_t)t * n_kv + kh) * head_dim + e];
+          kp[k_row(kh, t, n_total, head_dim) + k_perm(e, head_dim)] = kcache[((size_t)t * n_kv + kh) * head_dim + e];
     for (int ch = 0; ch < n_kv * head_dim; ch++)
       for (int t = 0; t < T; t++) vp[(size_t)ch * cp + v_perm(t)] = vcache[(size_t)ch * T + t];
     // the kernel fuses RoPE + KV store for the current position: feed it an identity rotation (cos 1, sin 0 is exact) and the

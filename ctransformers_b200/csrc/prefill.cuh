@@ -366,7 +366,7 @@ __device__ __forceinline__ void pb_kv_phase(const PPhase& ph, int n_tok) {
     const float* vsrc = a.v + (size_t)tok * a.kv_stride + (size_t)kh * a.hd;
     float o0, o1;
     rope_pair(__ldcg(ksrc + i0), __ldcg(ksrc + i1), cs, a.neox, o0, o1);
-    uint16_t* kd = a.kc + ((size_t)pos * a.n_kv + kh) * a.hd;
+    uint16_t* kd = a.kc + k_row(kh, pos, a.n_ctx, a.hd);
     kd[k_perm(i0, a.hd)] = f2h(o0);
     kd[k_perm(i1, a.hd)] = f2h(o1);
     uint16_t* vd = a.vc + (size_t)kh * a.hd * cp + v_perm(pos);

@@ -193,17 +193,16 @@ __device__ __forceinline__ int scale_fold8(int d0, int d1, int d2, int d3, int d
 struct Terms { float p[4]; float pm[2]; float dd[2]; float ddm[2]; };
 
 __device__ __forceinline__ void load_b_operands(const StAct& a, int b, int g, int t, uint32_t (&bA)[8], uint32_t (&bB)[8]) {
-  // block-diagonal B: thread (g, t) holds rows 4t..4t+3 / 16+4t.. of column g, which are non-zero only for g == t / g == t+4
-#pragma unroll
-  for (int s = 0; s < 8; s++) { bA[s] = 0u; bB[s] = 0u; }
-  if (g == t) {
-    const int4 lo = *(const int4*)(a.qs + b * 256 + t * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + t * 16);
-    bA[0] = lo.x; bA[1] = lo.y; bA[2] = lo.z; bA[3] = lo.w; bA[4] = hi.x; bA[5] = hi.y; bA[6] = hi.z; bA[7] = hi.w;
-  }
-  if (g == t + 4) {
-    const int4 lo = *(const int4*)(a.qs + b * 256 + g * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + g * 16);
-    bB[0] = lo.x; bB[1] = lo.y; bB[2] = lo.z; bB[3] = lo.w; bB[4] = hi.x; bB[5] = hi.y; bB[6] = hi.z; bB[7] = hi.w;
-  }
+  // block-diagonal B: thread (g, t) holds rows 4t..4t+3 / 16+4t.. of column g, which are non-zero only for g == t / g == t+4.
+  // Branch-free (every lane loads, the off-diagonal lanes select zero) so that ptxas can interleave the blocks of an item.
+  const int l = g & 3;   // the AVX lane whose words this thread would need: l = t for the diagonal lanes, l + 4 for the second half
+  const int4 lo = *(const int4*)(a.qs + b * 256 + g * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + g * 16);
+  const uint32_t mA = (g == t) ? 0xffffffffu : 0u, mB = (g == t + 4) ? 0xffffffffu : 0u;
+  (void)l;
+  bA[0] = (uint32_t)lo.x & mA; bA[1] = (uint32_t)lo.y & mA; bA[2] = (uint32_t)lo.z & mA; bA[3] = (uint32_t)lo.w & mA;
+  bA[4] = (uint32_t)hi.x & mA; bA[5] = (uint32_t)hi.y & mA; bA[6] = (uint32_t)hi.z & mA; bA[7] = (uint32_t)hi.w & mA;
+  bB[0] = (uint32_t)lo.x & mB; bB[1] = (uint32_t)lo.y & mB; bB[2] = (uint32_t)lo.z & mB; bB[3] = (uint32_t)lo.w & mB;
+  bB[4] = (uint32_t)hi.x & mB; bB[5] = (uint32_t)hi.y & mB; bB[6] = (uint32_t)hi.z & mB; bB[7] = (uint32_t)hi.w & mB;
 }
 
 template <int TYPE>
@@ -285,13 +284,14 @@ __device__ __forceinline__ void block_terms<GT_Q5_K>(const uint8_t* blk, int b, 
       r.p[i] = (float)scale_fold8(D[0][i], D[1][i], D[2][i], D[3][i], D[4][i], D[5][i], D[6][i], D[7][i], sc03, sc47);
     }
     r.dd[rr] = __fmul_rn(yd, h2f((uint16_t)((uint32_t)h.x & 0xffffu)));
-    if (rr == (t & 1)) {   // the scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]), kept by thread t = rr of the row's quad
+    {   // the scalar mins term of the AVX2 kernel: Σ_k m[k]·(bsums[2k]+bsums[2k+1]), kept by thread t = rr of the row's quad
       int hs = __dp2a_lo((int)pw.x, (int)m03, 0);
       hs = __dp2a_hi((int)pw.y, (int)m03, hs);
       hs = __dp2a_lo((int)pw.z, (int)m47, hs);
       hs = __dp2a_hi((int)pw.w, (int)m47, hs);
-      r.pm[0] = (float)hs;
-      r.ddm[0] = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)h.x >> 16)));
+      const float pmv = (float)hs, dmv = __fmul_rn(-yd, h2f((uint16_t)((uint32_t)h.x >> 16)));
+      if (rr == 0) { r.pm[0] = pmv; r.ddm[0] = dmv; }
+      else { r.pm[0] = (t & 1) ? pmv : r.pm[0]; r.ddm[0] = (t & 1) ? dmv : r.ddm[0]; }
     }
   }
 }
@@ -360,9 +360,16 @@ __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_ba
                                          volatile float* mail, volatile int* flag, const MVSeg& sg, const MVParams& p, int row0) {
   constexpr int KB = StTraits<TYPE>::KB, BB = StTraits<TYPE>::BB, NM = StTraits<TYPE>::NM;
   Terms tr[KB];
+  if (nblk == KB) {   // the common case, straight-line: the KB blocks are independent until the fold, ptxas interleaves them
 #pragma unroll
-  for (int i = 0; i < KB; i++)
-    if (i < nblk) block_terms<TYPE>(slot + i * BB, b0 + i, a, lane, tr[i]);
+    for (int i = 0; i < KB; i++) block_terms<TYPE>(slot + i * BB, b0 + i, a, lane, tr[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < KB; i++) {
+      if (i < nblk) block_terms<TYPE>(slot + i * BB, b0 + i, a, lane, tr[i]);
+      else { Terms z{}; tr[i] = z; }
+    }
+  }
   __syncwarp();
   if (lane == 0) mbar_arrive(empty_bar);   // every lane has its weight words in registers: the producer may refill the slot
 
@@ -378,7 +385,7 @@ __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_ba
   }
 #pragma unroll
   for (int i = 0; i < KB; i++) {
-    if (i < nblk) {
+    if (i < nblk) {   // (a skipped block must not touch the accumulators: fma(0, 0, -0.0f) would flip a sign bit)
       // one fmadd per block and AVX lane, blocks in order (k_quants.c:2706, 3253, 3864); mins: 2699-2701 (Q4_K), 3199-3201 (Q5_K)
 #pragma unroll
       for (int q = 0; q < 4; q++) acc[q] = __fmaf_rn(tr[i].dd[q >> 1], tr[i].p[q], acc[q]);
@@ -470,6 +477,7 @@ struct PickParams { const float* logits; int* state; int* out_tokens; int n; };
 struct alignas(16) Phase {
   int kind;
   int q6;           // PH_MATVEC: some matrix of the phase is Q6_K (the activation staging then also builds cneg)
+  const int* bounds;   // PH_MATVEC: [grid + 1] first tile of every CTA (TileSpace::boundary, computed once on the host: step_bounds)
   MVParams mv;      // PH_MATVEC
   AttnParams at;    // PH_ATTN
   EmbedParams em;   // PH_EMBED
@@ -500,8 +508,7 @@ __device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParam
     ti.seg = ts.locate(tl);
     ti.til = tl;
     ti.type = ti.seg == 0 ? p.seg[0].w.type : (ti.seg == 1 ? p.seg[1].w.type : p.seg[2].w.type);
-    const int kb = st_chunk_blocks(ti.type);
-    ti.nch = (nb + kb - 1) / kb;
+    ti.nch = ti.type == GT_Q4_K ? (nb + 3) >> 2 : (nb + 2) / 3;   // ceil(nb / st_chunk_blocks)
   }
   return ti;
 }
@@ -517,7 +524,7 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
     const MVParams& p = ph->mv;
     TileSpace ts;
     ts.init(p);
-    const int T0 = ts.boundary(blockIdx.x, gridDim.x), T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
+    const int T0 = __ldg(ph->bounds + blockIdx.x), T1 = __ldg(ph->bounds + blockIdx.x + 1);
     const int nb = p.K >> 8;
     for (int w0 = T0; w0 < T1; w0 += ST_MAXT) {
       const int ntw = min(ST_MAXT, T1 - w0);
@@ -548,7 +555,7 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
 
 // Consumer side of one mat-vec phase.  `seq` is the running item number (identical in every warp and in the producer).
 __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& np, uint8_t* ring, uint8_t* act_smem, double* red, uint64_t* full_bar, uint64_t* empty_bar,
-                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, unsigned long long* tr) {
+                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, const int* tb, unsigned long long* tr) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0);
@@ -557,8 +564,8 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
   bool first_item = tr != nullptr && threadIdx.x == 0;
   TileSpace ts;
   ts.init(p);
-  const int T0 = ts.boundary(blockIdx.x, gridDim.x), T1 = ts.boundary(blockIdx.x + 1, gridDim.x);
   const int nb = p.K >> 8;
+  const int T0 = tb[0], T1 = tb[1];
 #pragma unroll 1
   for (int w0 = T0; w0 < T1; w0 += ST_MAXT) {
     if (w0 != T0) {   // the mailboxes are re-used by the next ST_MAXT tiles
@@ -575,7 +582,9 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
       const int cnt = __popc(mask);
 #pragma unroll 1
       for (int r = (int)(((uint32_t)warp + ST_W - seq % ST_W) % ST_W); r < cnt; r += ST_W) {
-        const int j = __fns(mask, 0, r + 1);
+        unsigned mr = mask;                       // the r-th set bit of mask = the tile (lane) of this item
+        for (int q = 0; q < r; q++) mr &= mr - 1;
+        const int j = __ffs(mr) - 1;
         const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
         const int nch = __shfl_sync(0xffffffffu, ti.nch, j);
         const uint32_t n = seq + (uint32_t)r, slot = n % S;
@@ -635,7 +644,8 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
   __shared__ int flags[ST_MAXT];
   __shared__ float pick_v[ST_W];
   __shared__ int pick_i[ST_W];
-  __shared__ __align__(16) Phase ph;
+  __shared__ __align__(16) Phase ph_s[2];   // this phase's descriptor and the next one's (fetched with cp.async a phase ahead)
+  __shared__ int tb_s[2][2];                // first / end tile of this CTA, same double buffering
   const int warp = threadIdx.x >> 5;
   uint8_t* ring = smem;
   uint8_t* act_smem = smem + (size_t)args.n_slots * ST_SLOT;
@@ -652,28 +662,39 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
   pdl_wait();
   const unsigned G = gridDim.x;
   uint32_t seq = 0;
+  // descriptor of phase ip -> ph_s[ip & 1]; issued one phase ahead so that no global round trip sits on the phase boundary
+  auto fetch_phase = [&](int ip) {
+    if (ip >= args.n_phases) return;
+    const uint4* src = (const uint4*)(args.prog + ip);
+    const uint32_t dst = st_smem(&ph_s[ip & 1]);
+    const int i = (int)threadIdx.x - 32;
+    if (i >= 0 && i < (int)(sizeof(Phase) / 16)) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch_phase(0);
 #pragma unroll 1
   for (int ip = 0; ip < args.n_phases; ip++) {
     bar_sync<ST_BAR, ST_NT>();                 // every consumer warp is done with the previous phase (its stores are issued)
-    if (threadIdx.x == 0 && ip > 0) { __threadfence(); atomicAdd(args.sync, 1u); }
-    {   // next phase descriptor → shared memory; fold flags cleared
-      const uint4* src = (const uint4*)(args.prog + ip);
-      uint4* dst = (uint4*)&ph;
-      for (int i = threadIdx.x - 32; i >= 0 && i < (int)(sizeof(Phase) / 16); i += ST_NT - 32) dst[i] = __ldg(src + i);
+    if (threadIdx.x == 0 && ip > 0) {          // grid barrier: one arrive, then poll — nothing else sits between the two
+      __threadfence();
+      atomicAdd(args.sync, 1u);
+      const unsigned target = (unsigned)ip * G;
+      while (ld_acquire_u32(args.sync) < target) { }
+    } else {
+      asm volatile("cp.async.wait_all;" ::: "memory");
       if (threadIdx.x < ST_MAXT) flags[threadIdx.x] = 0;
     }
     bar_sync<ST_BAR, ST_NT>();
+    const Phase& ph = ph_s[ip & 1];
+    if (ph.kind == PH_MATVEC && threadIdx.x < 2) tb_s[ip & 1][threadIdx.x] = __ldg(ph.bounds + blockIdx.x + threadIdx.x);
+    fetch_phase(ip + 1);
     NormPre np;
-    if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);   // constants: fetched while the barrier completes
-    if (threadIdx.x == 0 && ip > 0) {
-      const unsigned target = (unsigned)ip * G;
-      while (ld_acquire_u32(args.sync) < target) { }
-    }
-    bar_sync<ST_BAR, ST_NT>();
+    if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);
     unsigned long long* const tr = args.trace ? args.trace + ((size_t)ip * G + blockIdx.x) * 4 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
     if (ph.kind == PH_MATVEC) {
-      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq, tr);
+      // (the tile bounds were written by threads 0/1 above; the barriers inside the activation staging order them)
+      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq, &tb_s[ip & 1][0], tr);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
       for (int task = blockIdx.x; task < n_tasks; task += G) {
@@ -723,6 +744,15 @@ inline StepLaunch step_launch_shape(const Phase* phases, int n, int n_sm, size_t
   L.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (max_dyn_smem - act) / ST_SLOT);
   L.smem = (size_t)L.n_slots * ST_SLOT + act;
   return L;
+}
+
+// first tile of every CTA of a mat-vec phase (the device reads it from Phase::bounds instead of redoing the 64-bit divisions)
+inline std::vector<int> step_bounds(const MVParams& p, int grid) {
+  TileSpace ts;
+  ts.init(p);
+  std::vector<int> b((size_t)grid + 1);
+  for (int c = 0; c <= grid; c++) b[c] = ts.boundary(c, grid);
+  return b;
 }
 
 // a mat-vec phase the step kernel can run: all matrices K-quant (→ Q8_K activations), K a multiple of 256
