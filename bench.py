@@ -3,19 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one single-token decode pass of the whole hot path (129 mat-vec launches over 225 weight tensors + 32 attention launches at a context of
-256..511 tokens).  Workload: synthetic 7B-shaped model (random valid quant blocks in the reference's Q4_K_M tensor mix,
+One "step" = one single-token decode pass of the whole hot path: ONE launch of the persistent step kernel (csrc/stream.cuh) whose
+phases are the 129 mat-vecs over 225 weight tensors, 32 attention blocks at a context of 256..511 tokens, the embedding row and the greedy pick.  Workload: synthetic 7B-shaped model (random valid quant blocks in the reference's Q4_K_M tensor mix,
 3.8 GB of weights ≫ the 126 MB L2, so every step streams its inputs from HBM — no L2 flush needed), 256-token prompt
 prefilled untimed, then W warm-up + K timed decode steps.
 
-  value     device-timed: K steps replayed as CUDA graphs with the token fed back on the device (k_argmax), CUDA events on the
-            launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling)
-  e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, logits D2H and the
-            host sampler inside the timed region
-  roofline  dominant kernel k_matvec (HBM-bound): the GGUF bytes of the weights its 129 launches of a step read (4005.4 MB) ÷ their
-            duration, measured live by replaying exactly those launches as a CUDA graph between CUDA events on the engine's
-            stream; peak = MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes per launch (profiles/k_matvec_traffic.json).
-            roofline.step = the same for the whole step (weights + KV + logits bytes ÷ device-timed step)
+  value     device-timed: K steps replayed as CUDA graphs with the token fed back on the device (the pick phase), CUDA events on the
+            launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling).  The
+            logits stay on the device (no D2H inside this number; e2e below includes the step's result read-back)
+  e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, the sampler's device half
+            (penalty + top-k), its candidates D2H and the host draw inside the timed region
+  roofline  dominant kernel k_step, mat-vec phases (HBM-bound): the GGUF bytes of the weights the 129 mat-vec phases of a step read
+            (4005.4 MB) ÷ the duration of a launch that holds exactly those phases (no attention / embedding / pick), measured live
+            as a CUDA graph between CUDA events on the engine's stream; peak = MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram
+            bytes (profiles/k_step_traffic.json).  roofline.step = the same for the whole step (weights + KV + logits bytes ÷
+            device-timed step)
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref/libctransformers_ref.so) on the host cores, same
             model file, same prompt, bounded sample, thread count swept (ggml's spin-wait pool collapses when oversubscribed).
 """
@@ -47,6 +49,9 @@ WORKLOADS = {
                      metric="decode tokens/s Falcon-7B Q5_K_M b=1", dtype="int8 (q5_K/q6_K/q8_0 weights x q8_K/q8_0 activations, dp4a), fp32 combine",
                      name="Falcon-7B-shaped (n_embd 4608, multi-query) Q5_K_M GGUF"),
 }
+# configs[2]: prompt ingestion of the same model (the batched kernel of csrc/prefill.cuh); a separate bench line, not the driver's
+WORKLOADS["prefill2048"] = dict(WORKLOADS["llama2-7b"], metric="prefill tokens/s Llama-2-7B Q4_K_M 2048-token prompt",
+                                dtype="int8 mma.sync (u8 scale digits x s8 Q8_K activations, exact int32), fp32 combine in the reference's order")
 WL = WORKLOADS["llama2-7b"]
 
 
@@ -85,8 +90,8 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag, self.proc = index, [], threading.Event(), None
 
     def run(self):
-        # one long-running nvidia-smi in loop mode (a sample every 50 ms) instead of one process per sample
-        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"]
+        # one long-running nvidia-smi in loop mode (a sample every 20 ms) instead of one process per sample
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "20"]
         try:
             self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
@@ -189,6 +194,61 @@ METRIC = WL["metric"]
 DTYPE = WL["dtype"]
 
 
+def run_prefill(args, path, rank, world, local, barrier, max_over_ranks, group):
+    """configs[2]: a 2048-token prompt through llm.eval(tokens, batch_size=512) — 4 reference-sized chunks, 64 batched launches of
+    32 tokens each (csrc/prefill.cuh) + the head mat-vec of the last token.  One "step" = one whole prompt."""
+    import numpy as np
+    from ctransformers_b200 import AutoModelForCausalLM, synth
+    n_prompt, ctx = 2048, 2304
+    llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=ctx)
+    shape = getattr(synth, WL["shape"])
+    ids = np.random.default_rng(1).integers(WL["lo"], shape.n_vocab, n_prompt).tolist()
+    ids[0] = 1
+    steps, W = max(1, min(args.steps, 8)), 1
+
+    def once():
+        llm._context = []
+        llm.eval(ids, batch_size=512)
+        return llm.ctb_llm_last_eval_ms()
+    for _ in range(W):
+        once()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = [once() for _ in range(steps)]
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.summary()
+    ms = max_over_ranks(sum(dev_ms))
+    tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    mk = 0   # Σ M·K over the mat-muls of a token
+    for (m, k, cnt) in ((shape.n_embd, shape.n_embd, 2), (shape.n_embd // shape.n_head * shape.n_head_kv, shape.n_embd, 2), (shape.n_ff, shape.n_embd, 2), (shape.n_embd, shape.n_ff, 1)):
+        mk += m * k * cnt * shape.n_layer
+    flops = 2.0 * n_prompt * mk
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    tf_peak = float(peaks.get("bf16_tflops", 1590.0))
+    achieved = flops / (ms / steps / 1e3) / 1e12
+    result = {
+        "metric": METRIC, "value": world * n_prompt * steps / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": W,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": WL["name"] + " (synthetic random quant blocks), one 2048-token prompt per step, llm.eval(tokens, batch_size=512), ctx 2304",
+                   "global_batch": world, "prompt": n_prompt, "batch_size": 512, "parallelism": f"replicas x{world}",
+                   "l2": "each batched launch streams the 3.8 GB of layer weights once: inputs exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": world * n_prompt * steps / wall, "unit": "tokens/s", "h2d_bytes_per_step": 64 * 33 * 16, "d2h_bytes_per_step": 4,
+                "how": "llm.eval(prompt, batch_size=512) wall clock per prompt: 64 state uploads of 33 x 16 B, the look-ahead pick read back"},
+        "gpu_launches": steps * (n_prompt // 32 + 1),
+        "roofline": {"bound": "tensor", "kernel": "k_pstep", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (no int8 figure is measured on this pool; the kernel's dense int8 mma.sync does 2 digit products per useful MAC)",
+                     "algorithmic_flops_per_step": flops, "how": "2 * N * sum(M*K) of the layer mat-muls / device-timed prompt"},
+        "first_token_after_prompt": int(tok),
+    }
+    if rank == 0:
+        print(json.dumps(result))
+    group.close()
+
+
 def workload_config(n):
     return {"workload": WL["name"] + " (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode",
             "global_batch": n, "ctx": CTX, "prompt": PROMPT, "parallelism": f"replicas x{n} (one sequence per GPU, no collective)",
@@ -230,6 +290,8 @@ def main():
 
     from ctransformers_b200 import AutoModelForCausalLM, synth
     path = ensure_model(rank, world, barrier)
+    if args.workload == "prefill2048":
+        return run_prefill(args, path, rank, world, local, barrier, max_over_ranks, group)
     llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=CTX)
     shape = getattr(synth, WL["shape"])
     ids = prompt_ids()
@@ -241,36 +303,38 @@ def main():
         llm.eval(ids, batch_size=256)
         return llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
 
+    # ------------------------------------------------------------------ end to end through the public API ("e2e")
+    # (first: the engine's look-ahead only runs while decoding appends to the cache, see Engine::after_eval)
+    tok = prefill()
+    for _ in range(W):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    e2e_tokens = []
+    for _ in range(steps):
+        llm.eval([tok])                                   # H2D {token, n_past}; stream sync
+        tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)   # device penalty + top-k, candidates D2H, host draw
+        e2e_tokens.append(tok)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = replicas.aggregate_tokens_per_s(world, steps, e2e_s * 1e3)
+    device_samples = int(llm.ctb_llm_device_samples())
+
     # ------------------------------------------------------------------ device-timed ("value")
     first = prefill()
     out = (C.c_int * (W + steps))()
     assert llm.ctb_llm_decode_greedy(first, PROMPT, W, out) >= 0                      # warm-up steps at n_past = 256..
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     ms = llm.ctb_llm_decode_greedy(int(out[W - 1]), PROMPT + W, steps, out)           # K timed steps, CUDA events inside
     barrier()
-    clocks = sampler.summary()
+    clocks = sampler.summary()                                                        # covers the e2e AND the device-timed region
     assert ms > 0
     ms = max_over_ranks(ms)
     tokens_dev = list(out[:steps])
     replicas_agree = all(t == tokens_dev for t in group.gather_ints(tokens_dev))   # every replica decodes the same sequence
     value = replicas.aggregate_tokens_per_s(world, steps, ms)
-
-    # ------------------------------------------------------------------ end to end through the public API ("e2e")
-    tok = prefill()
-    for _ in range(W):
-        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_tokens = []
-    for _ in range(steps):
-        llm.eval([tok])                                   # H2D {token, n_past}; D2H logits + hidden state; stream sync
-        tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
-        e2e_tokens.append(tok)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e = replicas.aggregate_tokens_per_s(world, steps, e2e_s * 1e3)
 
     # ------------------------------------------------------------------ roofline
     peak, peak_src = hbm_peak()
@@ -284,26 +348,26 @@ def main():
     prof_steps = 4
     for i in range(prof_steps):
         llm.ctb_llm_profile_step(tokens_dev[i], PROMPT + W + steps // 2 + i - prof_steps, ms_kind, cnt_kind)
-    # dominant kernel = k_matvec: its launches of one step alone, replayed as a CUDA graph between two CUDA events on the
-    # engine's stream (after everything else, so the KV cache it leaves behind does not matter)
+    # dominant kernel = k_step's mat-vec phases: a launch holding exactly those, replayed as a CUDA graph between two CUDA events
+    # on the engine's stream (after everything else, so the KV cache it leaves behind does not matter)
     n_mv = C.c_long(0)
     mv_ms = llm.ctb_llm_time_matvec_only(32, C.byref(n_mv))
     mv_ms = max_over_ranks(mv_ms)
     n_mv = max(1, n_mv.value)
     mv_achieved = wbytes / (mv_ms / 1e3) / 1e9
     traffic = None
-    tf = ROOT / "profiles" / "k_matvec_traffic.json"
+    tf = ROOT / "profiles" / "k_step_traffic.json"
     if tf.exists() and args.workload == "llama2-7b":
-        traffic = json.loads(tf.read_text()).get("dram_bytes_per_launch_avg")
+        traffic = json.loads(tf.read_text()).get("dram_bytes_per_matvec_phase_avg")
     roofline = {
-        "bound": "hbm", "kernel": "k_matvec", "achieved": mv_achieved, "peak": peak, "unit": "GB/s", "frac": mv_achieved / peak, "traffic": traffic,
-        "peak_source": peak_src, "launches_per_step": n_mv, "algorithmic_bytes_per_launch": wbytes / n_mv, "avg_launch_us": 1e3 * mv_ms / n_mv,
-        "how": "weight bytes of the step's k_matvec launches / their duration: the same launches (no attention, embedding, argmax) replayed as a CUDA graph, CUDA events on the launching stream, 32 replays",
+        "bound": "hbm", "kernel": "k_step (mat-vec phases)", "achieved": mv_achieved, "peak": peak, "unit": "GB/s", "frac": mv_achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "matvec_phases_per_step": n_mv, "algorithmic_bytes_per_phase": wbytes / n_mv, "avg_phase_us": 1e3 * mv_ms / n_mv,
+        "how": "weight bytes of the step's mat-vec phases / the duration of a k_step launch holding exactly those phases (no attention, embedding, pick), replayed as a CUDA graph, CUDA events on the launching stream, 32 replays; traffic = ncu dram bytes per phase",
         "step": {"achieved": achieved, "frac": achieved / peak, "bytes_per_step": step_bytes, "weight_bytes_per_step": wbytes,
                  "frac_vs_3.9GB_weights_only": (3.9e9 / (ms / 1e3 / steps) / 1e9) / peak,
                  "how": "weights + KV + logits bytes of a whole decode step / device-timed step (all kernels)"},
         "eager_ms_per_step_by_kind": {"matvec": ms_kind[0] / prof_steps, "attention": ms_kind[1] / prof_steps, "other": ms_kind[3] / prof_steps,
-                                      "how": f"eager pass, CUDA event after every kernel, {prof_steps} steps (kernel share of the step)"},
+                                      "how": f"un-fused eager pass (one kernel per op), CUDA event after every kernel, {prof_steps} steps (share of the step by op class)"},
     }
 
     result = {
@@ -311,9 +375,10 @@ def main():
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": shape.n_vocab * 4 + shape.n_embd * 4,
-                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs",
-                "lookahead_hits": int(llm.ctb_llm_speculative_hits())},
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16 + 64 * 4, "d2h_bytes_per_step": 4 + 2064,
+                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs; per step: H2D {token, position} and the 64-token repetition window, D2H the look-ahead pick and the sampler's candidate block (logits stay on the device until llm.logits is asked for)",
+                "lookahead_hits": int(llm.ctb_llm_speculative_hits()), "device_samples": device_samples},
+        "value_excludes": "logits D2H (kept on the device; e2e includes the step's result read-back)",
         "gpu_launches": int(llm.ctb_llm_launches_per_token()) * steps,
         "roofline": roofline,
         "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps], "replicas_agree": replicas_agree,
@@ -323,8 +388,8 @@ def main():
         del llm
         cores = os.cpu_count() or 1
         ref = AutoModelForCausalLM.from_pretrained(str(path), lib=str(REF_SO), context_length=CTX, threads=min(cores, 16))
-        n_prompt, n_dec = 32, 12
-        ref.eval(ids[:n_prompt], batch_size=32, threads=min(cores, 32))
+        n_prompt, n_dec = PROMPT, 12
+        ref.eval(ids[:n_prompt], batch_size=256, threads=min(cores, 32))
         t = ref.sample(top_k=1, repetition_penalty=1.0, seed=0)
         threads, sweep = pick_threads(ref, t, cores)
         t0 = time.perf_counter()

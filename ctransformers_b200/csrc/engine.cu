@@ -22,10 +22,32 @@ namespace ctb {
     cudaError_t e__ = (expr);                                                                                  \
     if (e__ != cudaSuccess)                                                                                    \
       throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + \
-                               std::to_string(__LINE__) + " (" #expr ")");                                     \
+                               std::to_string(__LINE__) + " (" #expr ")" + watchdog_note());                   \
   } while (0)
 
+// what a trapped persistent kernel left in the host-mapped watchdog words (stream.cuh st_fail)
+static int* g_watchdog_words = nullptr;
+static std::string watchdog_note() {
+  const int* d = g_watchdog_words;
+  if (!d || d[0] == 0) return "";
+  return " [step-kernel watchdog: wait " + std::to_string(d[0]) + " timed out in CTA " + std::to_string(d[1]) + ", aux " + std::to_string(d[2]) + ", thread " +
+         std::to_string(d[3]) + "]";
+}
+
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// the engine works on its own device but leaves the caller's current device as it found it
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e) + " (cudaSetDevice)");
+    }
+  }
+  ~DeviceGuard() { int cur = -1; cudaGetDevice(&cur); if (prev >= 0 && cur != prev) cudaSetDevice(prev); }
+};
 
 // one op of the per-token schedule: a phase of the step kernel, or (mat-vecs over non-K-quant weights) a kernel of its own
 struct StepOp {
@@ -44,6 +66,25 @@ __global__ void k_advance(int* state, int* out_tokens) {
   state[2] += 1;
   state[3] = state[1] + 1;   // a single-token eval: the attention rows have length position + 1
 }
+
+// ---- batched prefill (prefill.cuh): the per-token schedule rewritten over PB_T-row buffers
+struct PrefillState {
+  std::vector<void*> bufs;          // cudaMalloc'ed
+  PPhase* d_prog = nullptr;
+  int n_phases = 0;
+  int* d_state = nullptr;           // [PB_T][4] + n_tok
+  int* h_state = nullptr;           // pinned, PF_RING launches deep
+  int h_next = 0;
+  float* x_final = nullptr;         // batched buffer that holds the last layer's output rows
+  int n_slots = 0;
+  size_t smem = 0;
+  bool ok = false, tried = false;
+  ~PrefillState() {
+    for (void* b : bufs) cudaFree(b);
+    if (h_state) cudaFreeHost(h_state);
+  }
+};
+constexpr int PF_RING = 64;
 
 constexpr size_t UP_CHUNK = (size_t)32 << 20;   // upload pipeline: chunk bytes and buffers in flight
 constexpr int UP_BUFS = 3;
@@ -348,6 +389,14 @@ void Engine::init(const GGUFFile& g) {
   if (const char* e = getenv("CTB_NO_PREFILL")) prefill_on_ = !(e[0] == '1');
   if (const char* e = getenv("CTB_PREFILL_MIN")) prefill_min_ = std::max(1, atoi(e));
   CTB_CUDA(cudaMallocHost(&h_spec_tok_, 16));
+  {   // the kernels' watchdog words: host memory the device can write and the host can read after a trapped launch
+    CTB_CUDA(cudaHostAlloc(&h_dbg_, 64, cudaHostAllocMapped));
+    memset(h_dbg_, 0, 64);
+    int* d = nullptr;
+    CTB_CUDA(cudaHostGetDevicePointer(&d, h_dbg_, 0));
+    CTB_CUDA(st_set_debug_words(d));
+    g_watchdog_words = h_dbg_;
+  }
   CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
@@ -369,6 +418,8 @@ void Engine::release() {
   if (d_tokens_out_) cudaFree(d_tokens_out_);
   if (arena_) cudaFree(arena_);
   if (h_spec_tok_) cudaFreeHost(h_spec_tok_);
+  if (h_dbg_) cudaFreeHost(h_dbg_);
+  h_dbg_ = nullptr;
   if (h_sample_) cudaFreeHost(h_sample_);
   h_sample_ = nullptr;
   if (ev_pick_) cudaEventDestroy(ev_pick_);
@@ -627,7 +678,7 @@ void Engine::mark(int kind) {
 
 // One eager decode step, one kernel per op (un-fused), a CUDA event around every kernel: the kernel classes' share of a step.
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
@@ -657,7 +708,7 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
 double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   if (!mask) mask = ~0u;
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   std::vector<StepOp> sel;
   for (int i = 0; i <= n_body_; i++)
     if (ops_[i].ph.kind == PH_MATVEC && ((mask >> ops_[i].mvk) & 1)) sel.push_back(ops_[i]);
@@ -695,7 +746,7 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
 // One fused decode step with the step kernel stamping %globaltimer per phase and CTA (4 stamps: barrier passed, input staged,
 // first weight item ready, phase done).  out: n_phases x {kind, mvk} then n_phases x n_cta x 4 stamps; returns n_phases or -(words needed).
 long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   const int n = n_body_ + 1;
   for (int i = 0; i < n; i++)
@@ -772,7 +823,9 @@ void Engine::build_graphs() {
 void Engine::after_eval(int next_pos) {
   spec_pending_ = false;
   spec_pos_ = -1;
-  if (!spec_on_ || next_pos >= hp_.n_ctx) return;
+  // the look-ahead step writes K/V slot next_pos: only when nothing valid can live there (append-only decoding).  A caller
+  // that re-evaluates an earlier position and later continues past it keeps its cache contents.
+  if (!spec_on_ || next_pos >= hp_.n_ctx || next_pos < kv_high_) return;
   k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
   k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
   CTB_CUDA(cudaMemcpyAsync(h_spec_tok_, d_state_, 4, cudaMemcpyDeviceToHost, stream_));
@@ -803,7 +856,7 @@ void Engine::decode_one(int token, int pos, int n_total, bool with_logits) {
 void Engine::host_views() {
   eager_ = true;
   if (host_fresh_) return;
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   CTB_CUDA(cudaMemcpyAsync(h_logits_, d_logits_keep_, (size_t)hp_.n_vocab * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaMemcpyAsync(h_embd_, d_embd_keep_, (size_t)hp_.n_embd * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaStreamSynchronize(stream_));
@@ -813,7 +866,7 @@ void Engine::host_views() {
 std::vector<float> Engine::logits_copy() {
   std::vector<float> v((size_t)hp_.n_vocab);
   if (host_fresh_) { memcpy(v.data(), h_logits_, v.size() * 4); return v; }
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   CTB_CUDA(cudaMemcpyAsync(v.data(), d_logits_keep_, v.size() * 4, cudaMemcpyDeviceToHost, stream_));
   CTB_CUDA(cudaStreamSynchronize(stream_));
   return v;
@@ -821,7 +874,7 @@ std::vector<float> Engine::logits_copy() {
 
 int Engine::topk_candidates(const int* last, int n_last, float penalty, int k, int* ids, float* logits) {
   if (n_last > SG_MAX_LAST || k < 1 || k > SG_MAX_OUT / 2) return -1;
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   if (!d_sample_) {
     d_sample_ = (SampleGpuOut*)alloc(sizeof(SampleGpuOut));
     d_last_ = (int*)alloc(SG_MAX_LAST * 4 + 16);
@@ -860,7 +913,7 @@ void Engine::finish_eval(int next_pos, bool hit) {
 
 void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, int n) {
   if (n <= 0) return;
-  CTB_CUDA(cudaSetDevice(device_));
+  DeviceGuard dev_guard(device_);
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   bool hit = false;
   if (spec_pos_ >= 0) {
@@ -876,6 +929,7 @@ void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, in
     spec_pos_ = -1;
   }
   CTB_CUDA(cudaEventRecord(ev0_, stream_));
+  for (int i = 0; i < n; i++) kv_high_ = std::max(kv_high_, pos[i] + 1);
   if (!hit) {
     int i = 0;
     while (i < n) {
@@ -898,25 +952,6 @@ void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, in
   }   // else: the step for this token at this position is already in the stream
   finish_eval(pos[n - 1] + 1, hit);
 }
-
-// ---- batched prefill (prefill.cuh): the per-token schedule rewritten over PB_T-row buffers
-struct PrefillState {
-  std::vector<void*> bufs;          // cudaMalloc'ed
-  PPhase* d_prog = nullptr;
-  int n_phases = 0;
-  int* d_state = nullptr;           // [PB_T][4] + n_tok
-  int* h_state = nullptr;           // pinned, PF_RING launches deep
-  int h_next = 0;
-  float* x_final = nullptr;         // batched buffer that holds the last layer's output rows
-  int n_slots = 0;
-  size_t smem = 0;
-  bool ok = false, tried = false;
-  ~PrefillState() {
-    for (void* b : bufs) cudaFree(b);
-    if (h_state) cudaFreeHost(h_state);
-  }
-};
-constexpr int PF_RING = 64;
 
 bool Engine::ensure_prefill() {
   if (!prefill_on_) return false;
@@ -1031,7 +1066,8 @@ double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (n_steps > tokens_out_cap_) throw std::runtime_error("decode_greedy: too many steps");
   if (n_past + n_steps > hp_.n_ctx) throw std::runtime_error("decode_greedy: would run past the context length");
-  CTB_CUDA(cudaSetDevice(device_));
+  kv_high_ = std::max(kv_high_, n_past + n_steps);
+  DeviceGuard dev_guard(device_);
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   h_state_[0] = first_token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));

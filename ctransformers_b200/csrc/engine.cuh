@@ -114,7 +114,9 @@ class Engine {
   // speculative next step (see after_eval)
   bool spec_on_ = true, spec_pending_ = false;
   int spec_pos_ = -1, spec_streak_ = 0;
+  int kv_high_ = 0;              // one past the highest position any eval has written
   int* h_spec_tok_ = nullptr;
+  int* h_dbg_ = nullptr;         // host-mapped watchdog words of the persistent kernels
   void after_eval(int next_pos);
   int sm_count_ = 148;
   long launches_per_step_ = 0;

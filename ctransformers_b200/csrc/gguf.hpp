@@ -189,6 +189,7 @@ class GGUFFile {
         } else {
           size_t es = scalar_size(v.arr_type);
           if (!es) throw std::runtime_error("GGUF: bad array element type");
+          if (v.arr_n > (size_ - pos_) / es) throw std::runtime_error("GGUF: truncated file");   // (no 64-bit wrap in es * n)
           need(es * v.arr_n);
           v.arr_data = base_ + pos_;
           pos_ += es * v.arr_n;
@@ -208,14 +209,22 @@ class GGUFFile {
       t.offset = rd<uint64_t>();
     }
     const uint64_t align = get_u32("general.alignment", 32);
+    if (align == 0 || (align & (align - 1)) != 0) throw std::runtime_error("GGUF: general.alignment must be a power of two");
     const size_t data_start = (pos_ + align - 1) / align * align;
+    if (data_start > size_) throw std::runtime_error("GGUF: truncated file");
     for (size_t i = 0; i < tensors.size(); i++) {
       auto& t = tensors[i];
       const int be = type_block_elems(t.type), bb = type_block_bytes(t.type);
       if (!be) throw std::runtime_error("GGUF: tensor '" + t.name + "' has unsupported type " + std::to_string(t.type));
       if (t.ne[0] % be) throw std::runtime_error("GGUF: tensor '" + t.name + "' row length not a multiple of its block size");
-      t.nbytes = t.ne[0] / be * bb * t.ne[1] * t.ne[2] * t.ne[3];
-      if (data_start + t.offset + t.nbytes > size_) throw std::runtime_error("GGUF: tensor '" + t.name + "' data out of file bounds");
+      // overflow-checked size: every factor is bounded by the file size before it is multiplied in
+      uint64_t nbytes = t.ne[0] / be * (uint64_t)bb;
+      for (int d = 1; d < 4; d++) {
+        if (t.ne[d] != 0 && nbytes > (uint64_t)size_ / t.ne[d]) throw std::runtime_error("GGUF: tensor '" + t.name + "' data out of file bounds");
+        nbytes *= t.ne[d];
+      }
+      t.nbytes = nbytes;
+      if (t.offset > size_ - data_start || t.nbytes > size_ - data_start - t.offset) throw std::runtime_error("GGUF: tensor '" + t.name + "' data out of file bounds");
       t.data = base_ + data_start + t.offset;
       index_[t.name] = i;
     }

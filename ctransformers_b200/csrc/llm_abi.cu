@@ -120,7 +120,9 @@ int ctransformers_llm_tokenize(LLM* llm, const char* text, const bool add_bos_to
 }
 
 const char* ctransformers_llm_detokenize(LLM* llm, const int token) {
-  llm->piece_buf = llm->vocab.piece(token);
+  try {
+    llm->piece_buf = llm->vocab.piece(token);
+  } catch (...) { llm->piece_buf.clear(); }   // nothing may cross the C ABI
   return llm->piece_buf.c_str();
 }
 

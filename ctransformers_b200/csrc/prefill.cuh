@@ -297,7 +297,7 @@ __device__ __forceinline__ void pb_producer(const PStepArgs& args, uint8_t* ring
             const uint8_t* base = seg == 0 ? p.seg[0].w.st : (seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
             const uint8_t* src = base + ((size_t)til * nb + (size_t)kc * kb) * bb;
             const uint32_t slot = seq % S, bytes = (uint32_t)(nblk * bb);
-            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u, 14, (int)seq);
             mbar_expect_tx(&full_bar[slot], bytes);
             bulk_g2s(ring + (size_t)slot * ST_SLOT, src, bytes, &full_bar[slot]);
           }
@@ -335,7 +335,7 @@ __device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8
         const int kb = st_chunk_blocks(my_type);
         const int b0 = kc * kb, nblk = min(kb, nb - b0);
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
-        mbar_wait(&full_bar[slot], (n / S) & 1u);
+        mbar_wait(&full_bar[slot], (n / S) & 1u, 15, (int)n);
         if (my_type == GT_Q4_K) pb_chunk<GT_Q4_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
         else if (my_type == GT_Q6_K) pb_chunk<GT_Q6_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
         else pb_chunk<GT_Q5_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
@@ -407,7 +407,10 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
     bar_sync<PB_BAR, PB_NT>();
     if (threadIdx.x == 0 && ip > 0) {
       const unsigned target = (unsigned)ip * G;
-      while (ld_acquire_u32(args.sync) < target) { }
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_u32(args.sync) < target) {
+        if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(12, ip);
+      }
     }
     bar_sync<PB_BAR, PB_NT>();
     const int n_tok = min(PB_T, ph.state[PB_T * 4]);

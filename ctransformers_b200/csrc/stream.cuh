@@ -117,7 +117,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(st_smem(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) { } }
+// Every spin in the persistent kernels is bounded: a wait that lasts longer than ST_WATCHDOG_NS writes {code, CTA, aux} into
+// host-mapped memory and traps — a protocol bug then ends as a launch failure with a message, not as a hung GPU.
+#ifndef ST_WATCHDOG_NS
+#define ST_WATCHDOG_NS 4000000000ull
+#endif
+static __device__ int* g_st_dbg = nullptr;   // set by the host (st_set_debug_words): 4 ints of mapped pinned host memory, or null
+static __device__ __noinline__ void st_fail(int code, int aux) {
+  int* d = g_st_dbg;
+  if (d) { d[0] = code; d[1] = (int)blockIdx.x; d[2] = aux; d[3] = (int)threadIdx.x; __threadfence_system(); }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code = 1, int aux = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  const unsigned long long t0 = globaltimer_ns();
+  while (!mbar_try_wait(bar, parity)) {
+    if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(code, aux);
+  }
+}
 // global → shared bulk copy (TMA, SASS UBLKCP), completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(st_smem(dst)), "l"(src), "r"(bytes), "r"(st_smem(bar)) : "memory");
@@ -375,7 +392,12 @@ __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_ba
 
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, accm[2] = {0.f, 0.f};
   if (kc > 0) {
-    if (lane == 0) while (*flag < kc) { }
+    if (lane == 0 && *flag < kc) {
+      const unsigned long long t0 = globaltimer_ns();
+      while (*flag < kc) {
+        if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(3, kc);
+      }
+    }
     __syncwarp();
     __threadfence_block();
 #pragma unroll
@@ -513,6 +535,211 @@ __device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParam
   return ti;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Attention phase.  The cached K rows and V channels a task needs are constants of the step (every position but the current
+// one was written by earlier launches), so they travel through the SAME ring as the weights: the producer queues them between
+// the QKV mat-vec's items and the output projection's, and by the time the grid barrier after QKV opens they sit in shared
+// memory.  What is left on the critical path is one L2 round trip for q/k/v, one for the exp table, and arithmetic.
+//   K item  up to rows_per_item consecutive cached rows of the task's KV head (head-major cache: one contiguous bulk copy)
+//   V item  cv of the task's ATTN_CH channels, nchv 256-position chunks each (one bulk copy per channel)
+struct AttnRing { int pos, T, lim, n_k, rpi, n_v, cv, nchv; };
+__device__ __forceinline__ AttnRing attn_ring_geom(const AttnParams& p) {
+  AttnRing g;
+  g.pos = p.state[1];
+  g.T = g.pos + 1;
+  g.rpi = ST_SLOT / (p.hd * 2);
+  if (g.pos >= p.n_ctx) { g.T = 0; g.lim = 0; g.n_k = 0; g.n_v = 0; g.cv = 1; g.nchv = 0; return g; }
+  const int n_total = max(g.T, min(p.state[3], p.n_ctx));
+  g.lim = min(g.T, n_total & ~31);
+  g.n_k = (g.pos + g.rpi - 1) / g.rpi;
+  g.nchv = (g.T + 255) >> 8;
+  g.cv = max(1, min(8, ST_SLOT / (g.nchv * 512)));
+  g.n_v = (ATTN_CH + g.cv - 1) / g.cv;
+  return g;
+}
+
+// producer side of one attention phase
+__device__ __forceinline__ void st_attn_produce(const AttnParams& p, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t& seq) {
+  const AttnRing g = attn_ring_geom(p);
+  const int n_cg = p.hd / ATTN_CH, n_tasks = p.n_head * n_cg, group = p.n_head / p.n_kv, cp = kv_ctx_pad(p.n_ctx);
+  for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
+    const int h = task / n_cg, cg = task % n_cg, kvh = h / group;
+    for (int i = 0; i < g.n_k; i++) {
+      const uint32_t slot = seq % S;
+      const int rows = min(g.rpi, g.pos - i * g.rpi);
+      mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+      mbar_expect_tx(&full_bar[slot], (uint32_t)(rows * p.hd * 2));
+      bulk_g2s(ring + (size_t)slot * ST_SLOT, p.kc + k_row(kvh, i * g.rpi, p.n_ctx, p.hd), (uint32_t)(rows * p.hd * 2), &full_bar[slot]);
+      seq++;
+    }
+    for (int iv = 0; iv < g.n_v; iv++) {
+      const uint32_t slot = seq % S;
+      const int nch = min(g.cv, ATTN_CH - iv * g.cv);
+      const uint32_t bytes = (uint32_t)(g.nchv * 512);
+      mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+      mbar_expect_tx(&full_bar[slot], bytes * nch);
+      for (int q = 0; q < nch; q++)
+        bulk_g2s(ring + (size_t)slot * ST_SLOT + (size_t)q * bytes, p.vc + ((size_t)kvh * p.hd + cg * ATTN_CH + iv * g.cv + q) * cp, bytes, &full_bar[slot]);
+      seq++;
+    }
+  }
+}
+
+// consumer side: one (head, channel group) task, K / V of the older positions read from the ring.  Same arithmetic, same
+// order as attn_body (attention.cuh), which stays the reference implementation of the un-fused path.
+__device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem, const uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t seq0,
+                                             const AttnRing& g, int h, int cg, float* red_f, double* red_d) {
+  constexpr int NW = ST_W;
+  const int hd = p.hd, per = hd >> 5;
+  const int pos = g.pos, T = g.T, lim = g.lim;
+  const int group = p.n_head / p.n_kv, kvh = h / group;
+  const bool kv_writer = (h % group) == 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cp = kv_ctx_pad(p.n_ctx);
+  float* sc = (float*)smem;                             // [cp] scores, then exp values
+  uint16_t* p16 = (uint16_t*)(smem + (size_t)cp * 4);   // [cp] f16 probabilities, V-permuted order
+  uint16_t* q16 = p16 + cp;                             // [hd] f16 rotated query, K-permuted order
+  uint16_t* k16 = q16 + hd;                             // [hd] f16 rotated key of this position
+  uint16_t* v16 = k16 + hd;                             // [hd] f16 value of this position
+  {  // RoPE (pairs) + f16 conversion of q, k, v for this position; K / V rows of this position go to the cache
+    const float* qv = p.q + (size_t)h * hd;
+    const float* kv = p.k + (size_t)kvh * hd;
+    const float* vv = p.v + (size_t)kvh * hd;
+    uint16_t* kd = p.kc + k_row(kvh, pos, p.n_ctx, hd);
+    for (int i = threadIdx.x; i < hd / 2; i += ST_NT) {
+      const float2 cs = p.rope[(size_t)pos * (hd / 2) + i];
+      const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
+      float o0, o1;
+      rope_pair(__ldcg(qv + i0), __ldcg(qv + i1), cs, p.neox, o0, o1);
+      q16[k_perm(i0, hd)] = f2h(o0); q16[k_perm(i1, hd)] = f2h(o1);
+      rope_pair(__ldcg(kv + i0), __ldcg(kv + i1), cs, p.neox, o0, o1);
+      const uint16_t h0 = f2h(o0), h1 = f2h(o1);
+      k16[k_perm(i0, hd)] = h0; k16[k_perm(i1, hd)] = h1;
+      if (kv_writer && cg == 0) { kd[k_perm(i0, hd)] = h0; kd[k_perm(i1, hd)] = h1; }
+    }
+    for (int c = threadIdx.x; c < hd; c += ST_NT) {
+      const uint16_t hv = f2h(__ldcg(vv + c));
+      v16[c] = hv;
+      if (kv_writer && c / ATTN_CH == cg) p.vc[((size_t)kvh * hd + c) * cp + v_perm(pos)] = hv;
+    }
+  }
+  bar_sync<ST_BAR, ST_NT>();
+  // ---- scores: K item i belongs to warp i % NW (which also frees its slot); the current position comes from k16
+  for (int i = warp; i < g.n_k; i += NW) {
+    const uint32_t n = seq0 + (uint32_t)i, slot = n % S;
+    const uint16_t* rows = (const uint16_t*)(ring + (size_t)slot * ST_SLOT);
+    const int r0 = i * g.rpi, nr = min(g.rpi, pos - r0);
+    mbar_wait(&full_bar[slot], (n / S) & 1u);
+    if (per == 4) {
+      const uint2 qq = *(const uint2*)(q16 + lane * 4);
+      const float q0 = h2f((uint16_t)(qq.x & 0xffff)), q1 = h2f((uint16_t)(qq.x >> 16)), q2 = h2f((uint16_t)(qq.y & 0xffff)), q3 = h2f((uint16_t)(qq.y >> 16));
+      for (int t0 = 0; t0 < nr; t0 += 8) {
+        uint2 kk[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) kk[j] = *(const uint2*)(rows + (size_t)min(t0 + j, nr - 1) * hd + lane * 4);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float s = 0.f;
+          s = __fmaf_rn(h2f((uint16_t)(kk[j].x & 0xffff)), q0, s);
+          s = __fmaf_rn(h2f((uint16_t)(kk[j].x >> 16)), q1, s);
+          s = __fmaf_rn(h2f((uint16_t)(kk[j].y & 0xffff)), q2, s);
+          s = __fmaf_rn(h2f((uint16_t)(kk[j].y >> 16)), q3, s);
+          s = attn_reduce_f32x8(s);
+          if (lane == 0 && t0 + j < nr) sc[r0 + t0 + j] = __fmul_rn(s, p.kq_scale);
+        }
+      }
+    } else {
+      for (int t = 0; t < nr; t++) {
+        const uint16_t* kr = rows + (size_t)t * hd + lane * per;
+        float s = 0.f;
+        for (int e = 0; e < per; e++) s = __fmaf_rn(h2f(kr[e]), h2f(q16[lane * per + e]), s);
+        s = attn_reduce_f32x8(s);
+        if (lane == 0) sc[r0 + t] = __fmul_rn(s, p.kq_scale);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[slot]);
+  }
+  if (warp == g.n_k % NW) {   // the current position
+    float s = 0.f;
+    for (int e = 0; e < per; e++) s = __fmaf_rn(h2f(k16[lane * per + e]), h2f(q16[lane * per + e]), s);
+    s = attn_reduce_f32x8(s);
+    if (lane == 0) sc[pos] = __fmul_rn(s, p.kq_scale);
+  }
+  bar_sync<ST_BAR, ST_NT>();
+  // ---- soft_max: max, fp16 exp table, fp64 sum, * (float)(1/sum)   (ggml.c:12047-12069)
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += ST_NT) mx = fmaxf(mx, sc[t]);
+  mx = warp_max(mx);
+  if (lane == 0) red_f[warp] = mx;
+  bar_sync<ST_BAR, ST_NT>();
+  mx = red_f[0];
+#pragma unroll
+  for (int w = 1; w < NW; w++) mx = fmaxf(mx, red_f[w]);
+  double sum = 0.0;
+  for (int t = threadIdx.x; t < T; t += ST_NT) {
+    const float val = h2f(__ldg(p.exp_tab + f2h(__fsub_rn(sc[t], mx))));
+    sc[t] = val;
+    sum += (double)val;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red_d[warp] = sum;
+  bar_sync<ST_BAR, ST_NT>();
+  sum = 0.0;
+#pragma unroll
+  for (int w = 0; w < NW; w++) sum += red_d[w];
+  const float inv = (float)(1.0 / sum);
+  const int t_end = (T + 255) & ~255;
+  for (int t = threadIdx.x; t < t_end; t += ST_NT) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
+  bar_sync<ST_BAR, ST_NT>();
+  // ---- V·P for this task's channels (lane part + the leftover positions added one by one in double, ggml.c:2415-2418)
+  const int n_vec_eff = lim;                          // positions below it go through the 32 lanes (lim = min(T, n_vec))
+  const int n_total = max(T, min(p.state[3], p.n_ctx));
+  const int n_vec = n_total & ~31;
+  const int left = T - n_vec;                         // <= 31; <= 0 when the eval chunk extends past this token
+  const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
+  for (int cc = warp; cc < ATTN_CH; cc += NW) {
+    const int c = cg * ATTN_CH + cc;
+    const int iv = cc / g.cv;
+    const uint32_t n = seq0 + (uint32_t)(g.n_k + iv), slot = n % S;
+    mbar_wait(&full_bar[slot], (n / S) & 1u);
+    const uint16_t* vrow = (const uint16_t*)(ring + (size_t)slot * ST_SLOT + (size_t)(cc % g.cv) * g.nchv * 512);
+    const uint16_t vcur = v16[c];
+    float s = 0.f;
+    for (int ch = 0; ch * 256 < n_vec_eff; ch++) {
+      const uint4 vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
+      const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
+      const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w}, pw[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int t = ch * 256 + 32 * i + lane;
+        if (t < n_vec_eff) {
+          uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          const uint16_t ph16 = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+          if (t == pos) vh = vcur;
+          s = __fmaf_rn(h2f(vh), h2f(ph16), s);
+        }
+      }
+    }
+    s = attn_reduce_f32x8(s);
+    double sumf = (double)s;
+    if (left > 0) {
+      const int t = n_vec + lane;
+      uint16_t vh = vrow[ch_left * 256 + lane * 8 + i_left];
+      const uint16_t ph16 = p16[ch_left * 256 + lane * 8 + i_left];
+      if (t == pos) vh = vcur;
+      const float term = __fmul_rn(h2f(vh), h2f(ph16));
+      for (int l = 0; l < left; l++) sumf += (double)__shfl_sync(0xffffffffu, term, l);
+    }
+    if (lane == 0) p.out[(size_t)h * hd + c] = (float)sumf;
+  }
+  bar_sync<ST_BAR, ST_NT>();
+  if (threadIdx.x < g.n_v) {
+    const uint32_t n = seq0 + (uint32_t)(g.n_k + threadIdx.x);
+    mbar_arrive(&empty_bar[n % S]);
+  }
+}
+
 // Producer warp: the same enumeration as the consumers, one bulk copy per item, as far ahead as the ring allows.
 __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar) {
   const int lane = threadIdx.x & 31;
@@ -520,6 +747,11 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
   uint32_t seq = 0;
   for (int ip = 0; ip < args.n_phases; ip++) {
     const Phase* ph = args.prog + ip;
+    if (ph->kind == PH_ATTN) {
+      if (lane == 0) st_attn_produce(ph->at, ring, full_bar, empty_bar, S, seq);
+      seq = __shfl_sync(0xffffffffu, seq, 0);
+      continue;
+    }
     if (ph->kind != PH_MATVEC) continue;
     const MVParams& p = ph->mv;
     TileSpace ts;
@@ -542,7 +774,7 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
             const uint8_t* base = seg == 0 ? p.seg[0].w.st : (seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
             const uint8_t* src = base + ((size_t)til * nb + (size_t)kc * kb) * bb;
             const uint32_t slot = seq % S, bytes = (uint32_t)(nblk * bb);
-            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u, 4, (int)seq);
             mbar_expect_tx(&full_bar[slot], bytes);
             bulk_g2s(ring + (size_t)slot * ST_SLOT, src, bytes, &full_bar[slot]);
           }
@@ -592,7 +824,7 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
         const int b0 = kc * kb, nblk = min(kb, nb - b0);
         const MVSeg& sg = p.seg[seg];
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
-        mbar_wait(&full_bar[slot], (n / S) & 1u);
+        mbar_wait(&full_bar[slot], (n / S) & 1u, 5, (int)n);
         if (first_item) { tr[2] = globaltimer_ns(); first_item = false; }
         volatile float* mail = mailbox[j];
         volatile int* flag = flags + j;
@@ -679,10 +911,13 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
       __threadfence();
       atomicAdd(args.sync, 1u);
       const unsigned target = (unsigned)ip * G;
-      while (ld_acquire_u32(args.sync) < target) { }
+      const unsigned long long t0 = globaltimer_ns();
+      while (ld_acquire_u32(args.sync) < target) {
+        if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(2, ip);
+      }
     } else {
       asm volatile("cp.async.wait_all;" ::: "memory");
-      if (threadIdx.x < ST_MAXT) flags[threadIdx.x] = 0;
+      if (threadIdx.x >= 32 && threadIdx.x < 32 + ST_MAXT) flags[threadIdx.x - 32] = 0;   // (thread 0 is busy with the grid barrier)
     }
     bar_sync<ST_BAR, ST_NT>();
     const Phase& ph = ph_s[ip & 1];
@@ -697,9 +932,11 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
       st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq, &tb_s[ip & 1][0], tr);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
+      const AttnRing ag = attn_ring_geom(ph.at);
       for (int task = blockIdx.x; task < n_tasks; task += G) {
         if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
-        attn_body<ST_NT, ST_BAR, false>(ph.at, act_smem, task / n_cg, 0, task % n_cg, ph.at.state);
+        if (ag.T > 0) st_attn_task(ph.at, act_smem, ring, full_bar, empty_bar, (uint32_t)args.n_slots, seq, ag, task / n_cg, task % n_cg, pick_v, red);
+        seq += (uint32_t)(ag.n_k + ag.n_v);
       }
     } else if (ph.kind == PH_EMBED) {
       if (blockIdx.x == 0) {
@@ -779,6 +1016,8 @@ static inline size_t step_max_dyn_smem() {
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   return (size_t)optin > fa.sharedSizeBytes ? (size_t)optin - fa.sharedSizeBytes : 0;
 }
+// point the kernels' watchdog at 4 ints of host-mapped memory (each translation unit has its own copy of the symbol)
+static inline cudaError_t st_set_debug_words(int* dev_ptr) { return cudaMemcpyToSymbol(g_st_dbg, &dev_ptr, sizeof(int*)); }
 static inline cudaError_t step_set_smem_limit(size_t bytes) { return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
 static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, int n_phases, unsigned* d_sync, bool pdl = false,

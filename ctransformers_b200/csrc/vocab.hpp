@@ -41,6 +41,9 @@ struct Vocab {
     const GGUFValue* types = g.find("tokenizer.ggml.token_type");
     if (!types) throw std::runtime_error("cannot find token type list in GGUF file");
     if (scores->arr_n < toks->arr_n || types->arr_n < toks->arr_n) throw std::runtime_error("tokenizer arrays have inconsistent lengths");
+    // gguf_type: 6 = float32, 5 = int32, 8 = string (the reference reads them with exactly these element types, llama.cpp:1657-1674)
+    if (toks->arr_type != 8 || scores->arr_type != 6 || types->arr_type != 5 || !scores->arr_data || !types->arr_data)
+      throw std::runtime_error("tokenizer arrays have unexpected element types");
 
     const std::string model = g.need_str("tokenizer.ggml.model");
     if (model == "gpt2") {
@@ -114,7 +117,7 @@ struct Vocab {
         return r;
       }
       case TT_UNKNOWN: return "\xe2\x96\x85";
-      case TT_BYTE: return std::string(1, (char)strtol(e.text.substr(3, 2).c_str(), nullptr, 16));
+      case TT_BYTE: return e.text.size() >= 5 ? std::string(1, (char)strtol(e.text.substr(3, 2).c_str(), nullptr, 16)) : std::string();   // "<0xNN>"
       default: return "";
     }
   }

@@ -141,12 +141,13 @@ class LLM:
         if add_bos_token is None:
             add_bos_token = self.model_type == "llama"
         raw = text.encode()
-        # The reference sizes this buffer len(text)+1 (llm.py:335-337) although BOS + the SPM "▁" prefix can yield
-        # len+2 tokens: its C side then writes one int past the end and Python silently drops the last token.  We keep
-        # the visible result (at most len+1 tokens) but give the library room, so nothing is written out of bounds.
+        # The reference sizes this buffer len(text)+1 ints — characters, not bytes (llm.py:335-337) — although BOS + the SPM "▁"
+        # prefix can yield len+2 tokens: its C side then writes one int past the end and the slice silently drops the last
+        # token.  We return exactly what the reference returns (at most len(text)+1 tokens) but give the library room, so
+        # nothing is written out of bounds.
         out = (c_int * (len(raw) + 8))()
         n = self.ctransformers_llm_tokenize(raw, add_bos_token, out)
-        return out[: min(n, len(raw) + 1)]
+        return out[: min(n, len(text) + 1)]
 
     def detokenize(self, tokens: Sequence[int], decode: bool = True) -> Union[str, bytes]:
         if isinstance(tokens, int):
@@ -179,7 +180,7 @@ class LLM:
         last_n = _pick(last_n_tokens, cfg.last_n_tokens)
         if last_n < 0:
             last_n = self.context_length
-        recent = self._context[-last_n:] if last_n else []
+        recent = self._context[-last_n:]   # (last_n == 0 selects the whole context, exactly like the reference's slice, llm.py:443)
         arr = (c_int * len(recent))(*recent)
         return self.ctransformers_llm_sample(arr, len(recent), _pick(top_k, cfg.top_k), _pick(top_p, cfg.top_p),
                                              _pick(temperature, cfg.temperature), _pick(repetition_penalty, cfg.repetition_penalty),

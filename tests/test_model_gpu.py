@@ -5,6 +5,7 @@ unmodified reference itself run live on the same file when oracle/_ref is presen
 Bar: the north star asks for logits within 1e-3 relative and identical greedy tokens; the kernels reproduce the
 reference's accumulation order, so these tests demand the stronger thing — logits, embeddings and tokens IDENTICAL to the
 reference's, bit for bit (LOGIT_TOL documents the contractual tolerance and is asserted first for a readable failure)."""
+import ctypes as C
 from pathlib import Path
 
 import numpy as np
