@@ -29,7 +29,8 @@ namespace ctb {
 static int* g_watchdog_words = nullptr;
 static std::string watchdog_note() {
   const int* d = g_watchdog_words;
-  if (!d || d[0] == 0) return "";
+  if (!d) return " [no watchdog words]";
+  if (d[0] == 0) return " [watchdog words clear]";
   return " [step-kernel watchdog: wait " + std::to_string(d[0]) + " timed out in CTA " + std::to_string(d[1]) + ", aux " + std::to_string(d[2]) + ", thread " +
          std::to_string(d[3]) + "]";
 }
@@ -593,7 +594,13 @@ void Engine::build_ops() {
   for (const StepOp& op : ops_) if (op.ph.kind != PH_MATVEC || op.stream) phs.push_back(op.ph);
   const StepLaunch sl = step_launch_shape(phs.data(), (int)phs.size(), sm_count_, step_max_dyn_smem());
   step_grid_ = sl.grid; step_slots_ = sl.n_slots; step_smem_ = sl.smem;
-  if (any_stream && step_slots_ < 2) throw std::runtime_error("model rows are too long for the step kernel's shared memory");
+  if (const char* e = getenv("CTB_ST_SLOTS")) {   // A/B knob: fewer ring slots = less prefetch in flight
+    const int want = atoi(e);
+    if (want >= ST_W && want < step_slots_ && want % ST_W == 0) { step_smem_ -= (size_t)(step_slots_ - want) * ST_SLOT; step_slots_ = want; }
+  }
+  const bool ring_attn = st_attn_ring_ok(hp_.n_ctx, step_slots_) && !getenv("CTB_NO_RING_ATTN");
+  for (StepOp& op : ops_) if (op.ph.kind == PH_ATTN) op.ph.q6 = ring_attn ? 1 : 0;
+  if (any_stream && step_slots_ < ST_W) throw std::runtime_error("model rows are too long for the step kernel's shared memory");
   if (any_stream) CTB_CUDA(step_set_smem_limit(step_smem_));
   else fused_ = false;
   d_prog_ = (Phase*)alloc((ops_.size() + 1) * sizeof(Phase), 256);
@@ -621,7 +628,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, in
       int j = i;
       while (j < n && capable(ops[j])) j++;
       mark(-1);
-      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, j - i, d_sync_, pdl_));
+      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, j - i, d_sync_));
       launches_per_step_++;
       mark(0);
       i = j;
@@ -654,7 +661,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, in
         break;
       default:
         if (op.stream) {
-          CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, 1, d_sync_, pdl_));
+          CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, 1, d_sync_));
         } else {
           const MVLaunch L = matvec_launch_shape(op.ph.mv, sm_count_);
           CTB_CUDA(launch_matvec_kernel(L, stream_, op.ph.mv, pdl_));
@@ -1028,7 +1035,7 @@ bool Engine::ensure_prefill() {
   CTB_CUDA(cudaMemcpy(P.d_prog, prog.data(), prog.size() * sizeof(PPhase), cudaMemcpyHostToDevice));
   const size_t work = pb_work_bytes(K_max, hp_.n_ctx, hp_.head_dim()), room = pstep_max_dyn_smem();
   if (work + 4 * (size_t)ST_SLOT > room) return false;
-  P.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (room - work) / ST_SLOT);
+  P.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (room - work) / ST_SLOT) / PB_TEAMS * PB_TEAMS;   // whole per-team sub-rings
   P.smem = (size_t)P.n_slots * ST_SLOT + work;
   CTB_CUDA(pstep_set_smem_limit(P.smem));
   P.ok = true;

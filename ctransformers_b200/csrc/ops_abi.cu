@@ -119,7 +119,7 @@ void run_phases(std::vector<Phase> phs) {
     OPS_CUDA(cudaMemcpy(bounds.back()->p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
     ph.bounds = bounds.back()->as<int>();
   }
-  if (L.n_slots < 2) throw std::runtime_error("rows too long for the step kernel's shared memory");
+  if (L.n_slots < ST_W) throw std::runtime_error("rows too long for the step kernel's shared memory");
   OPS_CUDA(step_set_smem_limit(L.smem));
   DevBuf dprog((phs.size() + 1) * sizeof(Phase));
   OPS_CUDA(cudaMemcpy(dprog.p, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));

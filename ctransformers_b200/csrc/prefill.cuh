@@ -269,10 +269,14 @@ __device__ __forceinline__ void pb_finish(const PBState& st, float* xch, int typ
 }
 
 // ---------------------------------------------------------------------------------------------
+// Ring addressing: every team has its own slots (team t's i-th item: slot (i % depth) * PB_TEAMS + t, phase parity (i / depth) & 1),
+// so the team that waits for an item is the one that consumed the slot's previous occupant (see st_slot in stream.cuh).
 __device__ __forceinline__ void pb_producer(const PStepArgs& args, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar) {
   const int lane = threadIdx.x & 31;
-  const uint32_t S = (uint32_t)args.n_slots;
-  uint32_t seq = 0;
+  const uint32_t D = (uint32_t)(args.n_slots / PB_TEAMS);
+  uint32_t cnt[PB_TEAMS];
+#pragma unroll
+  for (int t = 0; t < PB_TEAMS; t++) cnt[t] = 0;
   for (int ip = 0; ip < args.n_phases; ip++) {
     const PPhase* ph = args.prog + ip;
     if (ph->kind != PP_GEMM) continue;
@@ -288,27 +292,28 @@ __device__ __forceinline__ void pb_producer(const PStepArgs& args, uint8_t* ring
         unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
         if (!mask) break;
         while (mask) {
-          const int j = __ffs(mask) - 1;
+          const int j = __ffs(mask) - 1;   // = the team
           mask &= mask - 1;
           const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
+          const uint32_t i = j == 0 ? cnt[0] : cnt[1];
           if (lane == 0) {
             const int kb = st_chunk_blocks(type), bb = st_block_bytes(type);
             const int nblk = min(kb, nb - kc * kb);
             const uint8_t* base = seg == 0 ? p.seg[0].w.st : (seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
             const uint8_t* src = base + ((size_t)til * nb + (size_t)kc * kb) * bb;
-            const uint32_t slot = seq % S, bytes = (uint32_t)(nblk * bb);
-            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u, 14, (int)seq);
+            const uint32_t slot = (i % D) * PB_TEAMS + (uint32_t)j, bytes = (uint32_t)(nblk * bb);
+            mbar_wait(&empty_bar[slot], ((i / D) & 1u) ^ 1u, 14, (int)i);
             mbar_expect_tx(&full_bar[slot], bytes);
             bulk_g2s(ring + (size_t)slot * ST_SLOT, src, bytes, &full_bar[slot]);
           }
-          seq++;
+          if (j == 0) cnt[0]++; else cnt[1]++;
         }
       }
     }
   }
 }
 
-__device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8_t* ring, float* xch_all, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t& seq) {
+__device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8_t* ring, float* xch_all, uint64_t* full_bar, uint64_t* empty_bar, uint32_t D, uint32_t& cnt) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, team = warp >> 2, lp = warp & 3;
   float* xch = xch_all + (size_t)team * (PB_XCH / 4);
@@ -331,18 +336,18 @@ __device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8
       const unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
       if (!mask) break;
       if ((mask >> team) & 1u) {
-        const uint32_t n = seq + (uint32_t)__popc(mask & ((1u << team) - 1u)), slot = n % S;
+        const uint32_t slot = (cnt % D) * PB_TEAMS + (uint32_t)team;
         const int kb = st_chunk_blocks(my_type);
         const int b0 = kc * kb, nblk = min(kb, nb - b0);
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
-        mbar_wait(&full_bar[slot], (n / S) & 1u, 15, (int)n);
+        mbar_wait(&full_bar[slot], (cnt / D) & 1u, 15, (int)cnt);
         if (my_type == GT_Q4_K) pb_chunk<GT_Q4_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
         else if (my_type == GT_Q6_K) pb_chunk<GT_Q6_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
         else pb_chunk<GT_Q5_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);   // 4 arrivals (the team's warps) free the slot
+        cnt++;
       }
-      seq += (uint32_t)__popc(mask);
     }
     if (team < ntw) {
       if (team == 0) pb_finish<2>(st, xch, my_type, lane, lp, threadIdx.x & 127, ph, n_tok, my_seg, my_til * ST_ROWS);
@@ -394,7 +399,7 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
     return;
   }
   const unsigned G = gridDim.x;
-  uint32_t seq = 0;
+  uint32_t seq = 0;   // this warp's team's item count
 #pragma unroll 1
   for (int ip = 0; ip < args.n_phases; ip++) {
     bar_sync<PB_BAR, PB_NT>();
@@ -415,7 +420,7 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
     bar_sync<PB_BAR, PB_NT>();
     const int n_tok = min(PB_T, ph.state[PB_T * 4]);
     if (ph.kind == PP_GEMM) {
-      pb_gemm_phase(ph, n_tok, ring, (float*)work, full_bar, empty_bar, (uint32_t)args.n_slots, seq);
+      pb_gemm_phase(ph, n_tok, ring, (float*)work, full_bar, empty_bar, (uint32_t)(args.n_slots / PB_TEAMS), seq);
     } else if (ph.kind == PP_QUANT) {
       for (int tok = blockIdx.x; tok < n_tok; tok += G) {
         MVParams q = ph.mv;

@@ -15,7 +15,7 @@
 //                   still wait at a grid barrier, stage an activation vector or run attention: HBM never idles.
 //   work item       (16-row tile, chunk of 3-4 consecutive 256-weight blocks): 16 x {144,176,210} bytes per block, contiguous
 //                   in the STREAM layout written at load time (k_repack_stream).  Items are numbered in one sequence that both
-//                   sides enumerate identically; item n lives in slot n % S and belongs to consumer warp n % ST_W.
+//                   sides enumerate identically; item n belongs to consumer warp n % ST_W and lives in one of that warp's slots.
 //   consumer warp   per block: the 8 (sub-block) x 8 (AVX lane) 4-element integer dots of 16 rows come from 8 tensor-core
 //                   instructions — mma.sync.m16n8k32 u8 x s8 with A = 16 rows x one 32-weight sub-block (nibbles unpacked in
 //                   registers) and B = that sub-block's int8 activations laid out BLOCK-DIAGONALLY (column l holds elements
@@ -34,13 +34,14 @@
 namespace ctb {
 
 #ifndef CTB_ST_WARPS
-#define CTB_ST_WARPS 11
+#define CTB_ST_WARPS 10
 #endif
 constexpr int ST_W = CTB_ST_WARPS;      // consumer warps
 constexpr int ST_NT = ST_W * 32;        // consumer threads (threads 0 .. ST_NT-1)
 constexpr int ST_THREADS = ST_NT + 32;  // + the producer warp
-constexpr int ST_SLOT = 10240;          // ring slot: holds 4 Q4_K / 3 Q5_K / 3 Q6_K blocks of a 16-row tile
-constexpr int ST_MAX_SLOTS = 20;
+constexpr int ST_SLOT = 9216;           // ring slot: holds 4 Q4_K / 3 Q5_K / 2 Q6_K blocks of a 16-row tile
+constexpr int ST_MAX_DEPTH = 2;         // slots per consumer warp; the ring has ST_W * depth slots
+constexpr int ST_MAX_SLOTS = ST_W * ST_MAX_DEPTH;
 constexpr int ST_MAXT = 16;             // tiles of a CTA whose fold chains are alive at the same time (one mailbox each)
 constexpr int ST_ROWS = 16;
 constexpr int ST_BAR = 1;               // named barrier of the consumer warps
@@ -48,7 +49,7 @@ constexpr int ST_STATE = 6;             // floats of fold state per thread: 4 AV
 
 __host__ __device__ inline int st_row_block_bytes(int type) { return type == GT_Q4_K ? 144 : (type == GT_Q5_K ? 176 : 210); }
 __host__ __device__ inline int st_block_bytes(int type) { return ST_ROWS * st_row_block_bytes(type); }   // 2304 / 2816 / 3360
-__host__ __device__ inline int st_chunk_blocks(int type) { return type == GT_Q4_K ? 4 : 3; }
+__host__ __device__ inline int st_chunk_blocks(int type) { return type == GT_Q4_K ? 4 : (type == GT_Q5_K ? 3 : 2); }
 __host__ __device__ inline int st_tile_cost(int type) { return type == GT_Q6_K ? 105 : (type == GT_Q5_K ? 88 : 72); }   // bytes per row-block / 2
 __host__ __device__ inline size_t st_matrix_bytes(int type, int M, int nb) { return (size_t)((M + ST_ROWS - 1) / ST_ROWS) * nb * st_block_bytes(type); }
 
@@ -103,6 +104,15 @@ static __global__ void k_repack_stream(int type, const uint8_t* __restrict__ raw
     st[idx] = row < (size_t)M ? *(const uint16_t*)(raw + (row * nb + b) * rbb + src) : (uint16_t)0;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Ring addressing.  Item n (one global sequence, enumerated identically by the producer and the consumers) belongs to
+// consumer warp n % ST_W and lives in one of THAT warp's own `depth` slots: slot = ((n / ST_W) % depth) * ST_W + n % ST_W,
+// mbarrier phase parity ((n / ST_W) / depth) & 1.  The warp that waits for item n is the warp that consumed the slot's
+// previous occupant, so it can never be a whole barrier phase ahead of the data (a parity wait cannot tell phase r from
+// phase r + 2: with slots shared between warps a fast warp saw "full" on a slot whose previous item was still landing).
+__device__ __forceinline__ uint32_t st_slot(uint32_t n, uint32_t depth) { return ((n / ST_W) % depth) * ST_W + n % ST_W; }
+__device__ __forceinline__ uint32_t st_parity(uint32_t n, uint32_t depth) { return ((n / ST_W) / depth) & 1u; }
 
 // ---------------------------------------------------------------------------------------------
 // PTX: mbarrier, bulk copy, tensor-core mma
@@ -367,7 +377,7 @@ __device__ __forceinline__ void block_terms<GT_Q6_K>(const uint8_t* blk, int b, 
 template <int TYPE> struct StTraits;
 template <> struct StTraits<GT_Q4_K> { static constexpr int KB = 4, BB = 2304, NM = 2; };
 template <> struct StTraits<GT_Q5_K> { static constexpr int KB = 3, BB = 2816, NM = 1; };
-template <> struct StTraits<GT_Q6_K> { static constexpr int KB = 3, BB = 3360, NM = 0; };
+template <> struct StTraits<GT_Q6_K> { static constexpr int KB = 2, BB = 3360, NM = 0; };
 
 // One work item: blocks [b0, b0 + nblk) of the 16-row tile whose pieces lie in `slot`.  Integer work first (the slot is
 // released as soon as the last weight word has been read), then the ordered fp32 fold: state in from the mailbox unless this
@@ -499,6 +509,7 @@ struct PickParams { const float* logits; int* state; int* out_tokens; int n; };
 struct alignas(16) Phase {
   int kind;
   int q6;           // PH_MATVEC: some matrix of the phase is Q6_K (the activation staging then also builds cneg)
+                    // PH_ATTN: 1 = cached K / V travel through the ring (st_attn_ring_ok), 0 = read from global memory (attn_body)
   const int* bounds;   // PH_MATVEC: [grid + 1] first tile of every CTA (TileSpace::boundary, computed once on the host: step_bounds)
   MVParams mv;      // PH_MATVEC
   AttnParams at;    // PH_ATTN
@@ -514,6 +525,11 @@ struct StepArgs {
   unsigned long long* trace;   // optional: per phase and CTA 4 globaltimer stamps {barrier passed, input staged, first item ready, phase done}
 };
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -530,7 +546,7 @@ __device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParam
     ti.seg = ts.locate(tl);
     ti.til = tl;
     ti.type = ti.seg == 0 ? p.seg[0].w.type : (ti.seg == 1 ? p.seg[1].w.type : p.seg[2].w.type);
-    ti.nch = ti.type == GT_Q4_K ? (nb + 3) >> 2 : (nb + 2) / 3;   // ceil(nb / st_chunk_blocks)
+    ti.nch = ti.type == GT_Q4_K ? (nb + 3) >> 2 : (ti.type == GT_Q5_K ? (nb + 2) / 3 : (nb + 1) >> 1);   // ceil(nb / st_chunk_blocks)
   }
   return ti;
 }
@@ -558,30 +574,37 @@ __device__ __forceinline__ AttnRing attn_ring_geom(const AttnParams& p) {
   return g;
 }
 
-// producer side of one attention phase
+// producer side of one attention phase (whole warp: lane i issues item i of a task's K run / V groups)
 __device__ __forceinline__ void st_attn_produce(const AttnParams& p, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar, uint32_t S, uint32_t& seq) {
+  const int lane = threadIdx.x & 31;
   const AttnRing g = attn_ring_geom(p);
   const int n_cg = p.hd / ATTN_CH, n_tasks = p.n_head * n_cg, group = p.n_head / p.n_kv, cp = kv_ctx_pad(p.n_ctx);
   for (int task = blockIdx.x; task < n_tasks; task += gridDim.x) {
     const int h = task / n_cg, cg = task % n_cg, kvh = h / group;
-    for (int i = 0; i < g.n_k; i++) {
-      const uint32_t slot = seq % S;
-      const int rows = min(g.rpi, g.pos - i * g.rpi);
-      mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
-      mbar_expect_tx(&full_bar[slot], (uint32_t)(rows * p.hd * 2));
-      bulk_g2s(ring + (size_t)slot * ST_SLOT, p.kc + k_row(kvh, i * g.rpi, p.n_ctx, p.hd), (uint32_t)(rows * p.hd * 2), &full_bar[slot]);
-      seq++;
+    const int step = min(32, ST_W * (int)S);   // lanes of one batch never share a slot (see st_producer)
+    for (int i0 = 0; i0 < g.n_k; i0 += step) {
+      const int i = i0 + lane;
+      if (lane < step && i < g.n_k) {
+        const uint32_t n = seq + (uint32_t)i, slot = st_slot(n, S);
+        const int rows = min(g.rpi, g.pos - i * g.rpi);
+        mbar_wait(&empty_bar[slot], st_parity(n, S) ^ 1u, 6, (int)n);
+        mbar_expect_tx(&full_bar[slot], (uint32_t)(rows * p.hd * 2));
+        bulk_g2s(ring + (size_t)slot * ST_SLOT, p.kc + k_row(kvh, i * g.rpi, p.n_ctx, p.hd), (uint32_t)(rows * p.hd * 2), &full_bar[slot]);
+      }
+      __syncwarp();
     }
-    for (int iv = 0; iv < g.n_v; iv++) {
-      const uint32_t slot = seq % S;
+    seq += (uint32_t)g.n_k;
+    for (int iv = lane; iv < g.n_v; iv += 32) {   // n_v <= 32 / cv <= S is checked on the host (st_attn_ring_ok)
+      const uint32_t n = seq + (uint32_t)iv, slot = st_slot(n, S);
       const int nch = min(g.cv, ATTN_CH - iv * g.cv);
       const uint32_t bytes = (uint32_t)(g.nchv * 512);
-      mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u);
+      mbar_wait(&empty_bar[slot], st_parity(n, S) ^ 1u, 7, (int)n);
       mbar_expect_tx(&full_bar[slot], bytes * nch);
       for (int q = 0; q < nch; q++)
         bulk_g2s(ring + (size_t)slot * ST_SLOT + (size_t)q * bytes, p.vc + ((size_t)kvh * p.hd + cg * ATTN_CH + iv * g.cv + q) * cp, bytes, &full_bar[slot]);
-      seq++;
     }
+    __syncwarp();
+    seq += (uint32_t)g.n_v;
   }
 }
 
@@ -625,11 +648,11 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
   }
   bar_sync<ST_BAR, ST_NT>();
   // ---- scores: K item i belongs to warp i % NW (which also frees its slot); the current position comes from k16
-  for (int i = warp; i < g.n_k; i += NW) {
-    const uint32_t n = seq0 + (uint32_t)i, slot = n % S;
+  for (int i = (int)(((uint32_t)warp + NW - seq0 % NW) % NW); i < g.n_k; i += NW) {   // K item i = ring item seq0 + i: its warp is (seq0 + i) % ST_W
+    const uint32_t n = seq0 + (uint32_t)i, slot = st_slot(n, S);
     const uint16_t* rows = (const uint16_t*)(ring + (size_t)slot * ST_SLOT);
     const int r0 = i * g.rpi, nr = min(g.rpi, pos - r0);
-    mbar_wait(&full_bar[slot], (n / S) & 1u);
+    mbar_wait(&full_bar[slot], st_parity(n, S), 8, (int)n);
     if (per == 4) {
       const uint2 qq = *(const uint2*)(q16 + lane * 4);
       const float q0 = h2f((uint16_t)(qq.x & 0xffff)), q1 = h2f((uint16_t)(qq.x >> 16)), q2 = h2f((uint16_t)(qq.y & 0xffff)), q3 = h2f((uint16_t)(qq.y >> 16));
@@ -660,7 +683,7 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[slot]);
   }
-  if (warp == g.n_k % NW) {   // the current position
+  if (warp == (int)((seq0 + (uint32_t)g.n_k) % NW)) {   // the current position
     float s = 0.f;
     for (int e = 0; e < per; e++) s = __fmaf_rn(h2f(k16[lane * per + e]), h2f(q16[lane * per + e]), s);
     s = attn_reduce_f32x8(s);
@@ -701,8 +724,8 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
   for (int cc = warp; cc < ATTN_CH; cc += NW) {
     const int c = cg * ATTN_CH + cc;
     const int iv = cc / g.cv;
-    const uint32_t n = seq0 + (uint32_t)(g.n_k + iv), slot = n % S;
-    mbar_wait(&full_bar[slot], (n / S) & 1u);
+    const uint32_t n = seq0 + (uint32_t)(g.n_k + iv), slot = st_slot(n, S);
+    mbar_wait(&full_bar[slot], st_parity(n, S), 9, (int)n);
     const uint16_t* vrow = (const uint16_t*)(ring + (size_t)slot * ST_SLOT + (size_t)(cc % g.cv) * g.nchv * 512);
     const uint16_t vcur = v16[c];
     float s = 0.f;
@@ -736,20 +759,19 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
   bar_sync<ST_BAR, ST_NT>();
   if (threadIdx.x < g.n_v) {
     const uint32_t n = seq0 + (uint32_t)(g.n_k + threadIdx.x);
-    mbar_arrive(&empty_bar[n % S]);
+    mbar_arrive(&empty_bar[st_slot(n, S)]);
   }
 }
 
 // Producer warp: the same enumeration as the consumers, one bulk copy per item, as far ahead as the ring allows.
 __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring, uint64_t* full_bar, uint64_t* empty_bar) {
   const int lane = threadIdx.x & 31;
-  const uint32_t S = (uint32_t)args.n_slots;
+  const uint32_t S = (uint32_t)(args.n_slots / ST_W);   // ring depth per consumer warp
   uint32_t seq = 0;
   for (int ip = 0; ip < args.n_phases; ip++) {
     const Phase* ph = args.prog + ip;
     if (ph->kind == PH_ATTN) {
-      if (lane == 0) st_attn_produce(ph->at, ring, full_bar, empty_bar, S, seq);
-      seq = __shfl_sync(0xffffffffu, seq, 0);
+      if (ph->q6) st_attn_produce(ph->at, ring, full_bar, empty_bar, S, seq);
       continue;
     }
     if (ph->kind != PH_MATVEC) continue;
@@ -762,24 +784,29 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
       const int ntw = min(ST_MAXT, T1 - w0);
       const TileInfo ti = tile_info(ts, p, w0 + lane, nb, lane < ntw);
       for (int kc = 0;; kc++) {
-        unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
+        const unsigned mask = __ballot_sync(0xffffffffu, kc < ti.nch);
         if (!mask) break;
-        while (mask) {
-          const int j = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
-          if (lane == 0) {
-            const int kb = st_chunk_blocks(type), bb = st_block_bytes(type);
+        // the items of this row are independent: every lane issues the copy of its own tile (a single issuing thread would cap
+        // the stream at one item per ~400 cycles — measured: exactly the 22 B/clk/SM the first build streamed at)
+        const int rank = __popc(mask & ((1u << lane) - 1u)), cnt = __popc(mask);
+        // at most S lanes at a time: two items of one batch never share a slot, so no lane waits for a slot that only another
+        // lane of the same (converged) warp could fill
+        for (int base = 0; base < cnt; base += ST_W * (int)S) {
+          if (((mask >> lane) & 1u) && rank >= base && rank < base + ST_W * (int)S) {
+            const uint32_t n = seq + (uint32_t)rank, slot = st_slot(n, S);
+            const int kb = st_chunk_blocks(ti.type), bb = st_block_bytes(ti.type);
             const int nblk = min(kb, nb - kc * kb);
-            const uint8_t* base = seg == 0 ? p.seg[0].w.st : (seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
-            const uint8_t* src = base + ((size_t)til * nb + (size_t)kc * kb) * bb;
-            const uint32_t slot = seq % S, bytes = (uint32_t)(nblk * bb);
-            mbar_wait(&empty_bar[slot], ((seq / S) & 1u) ^ 1u, 4, (int)seq);
+            const uint8_t* base_p = ti.seg == 0 ? p.seg[0].w.st : (ti.seg == 1 ? p.seg[1].w.st : p.seg[2].w.st);
+            const uint8_t* src = base_p + ((size_t)ti.til * nb + (size_t)kc * kb) * bb;
+            const uint32_t bytes = (uint32_t)(nblk * bb);
+            mbar_wait(&empty_bar[slot], st_parity(n, S) ^ 1u, 4, (int)n);
             mbar_expect_tx(&full_bar[slot], bytes);
             bulk_g2s(ring + (size_t)slot * ST_SLOT, src, bytes, &full_bar[slot]);
           }
-          seq++;
+          __syncwarp();
         }
+        __syncwarp();
+        seq += (uint32_t)__popc(mask);
       }
     }
   }
@@ -819,12 +846,12 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
         const int j = __ffs(mr) - 1;
         const int seg = __shfl_sync(0xffffffffu, ti.seg, j), til = __shfl_sync(0xffffffffu, ti.til, j), type = __shfl_sync(0xffffffffu, ti.type, j);
         const int nch = __shfl_sync(0xffffffffu, ti.nch, j);
-        const uint32_t n = seq + (uint32_t)r, slot = n % S;
+        const uint32_t n = seq + (uint32_t)r, slot = st_slot(n, S);
         const int kb = st_chunk_blocks(type);
         const int b0 = kc * kb, nblk = min(kb, nb - b0);
         const MVSeg& sg = p.seg[seg];
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
-        mbar_wait(&full_bar[slot], (n / S) & 1u, 5, (int)n);
+        mbar_wait(&full_bar[slot], st_parity(n, S), 5, (int)n);
         if (first_item) { tr[2] = globaltimer_ns(); first_item = false; }
         volatile float* mail = mailbox[j];
         volatile int* flag = flags + j;
@@ -887,11 +914,11 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
   }
   __syncthreads();
   pdl_trigger();
-  if (warp == ST_W) {   // weights are constants of the model: the stream starts before the predecessor kernel has finished
+  pdl_wait();           // (the producer reads device state too: the position decides how many K / V items an attention phase has)
+  if (warp == ST_W) {
     st_producer(args, ring, full_bar, empty_bar);
     return;
   }
-  pdl_wait();
   const unsigned G = gridDim.x;
   uint32_t seq = 0;
   // descriptor of phase ip -> ph_s[ip & 1]; issued one phase ahead so that no global round trip sits on the phase boundary
@@ -907,14 +934,16 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
 #pragma unroll 1
   for (int ip = 0; ip < args.n_phases; ip++) {
     bar_sync<ST_BAR, ST_NT>();                 // every consumer warp is done with the previous phase (its stores are issued)
-    if (threadIdx.x == 0 && ip > 0) {          // grid barrier: one arrive, then poll — nothing else sits between the two
-      __threadfence();
-      atomicAdd(args.sync, 1u);
+    if (threadIdx.x == 0 && ip > 0) {          // grid barrier: one release-arrive, relaxed polls, one acquire fence at the end
       const unsigned target = (unsigned)ip * G;
-      const unsigned long long t0 = globaltimer_ns();
-      while (ld_acquire_u32(args.sync) < target) {
-        if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(2, ip);
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(args.sync) : "memory");
+      if (ld_relaxed_u32(args.sync) < target) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_relaxed_u32(args.sync) < target) {
+          if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(2, ip);
+        }
       }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_all;" ::: "memory");
       if (threadIdx.x >= 32 && threadIdx.x < 32 + ST_MAXT) flags[threadIdx.x - 32] = 0;   // (thread 0 is busy with the grid barrier)
@@ -929,14 +958,21 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
     if (ph.kind == PH_MATVEC) {
       // (the tile bounds were written by threads 0/1 above; the barriers inside the activation staging order them)
-      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)args.n_slots, seq, &tb_s[ip & 1][0], tr);
+      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)(args.n_slots / ST_W), seq, &tb_s[ip & 1][0], tr);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
-      const AttnRing ag = attn_ring_geom(ph.at);
-      for (int task = blockIdx.x; task < n_tasks; task += G) {
-        if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
-        if (ag.T > 0) st_attn_task(ph.at, act_smem, ring, full_bar, empty_bar, (uint32_t)args.n_slots, seq, ag, task / n_cg, task % n_cg, pick_v, red);
-        seq += (uint32_t)(ag.n_k + ag.n_v);
+      if (ph.q6) {
+        const AttnRing ag = attn_ring_geom(ph.at);
+        for (int task = blockIdx.x; task < n_tasks; task += G) {
+          if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
+          if (ag.T > 0) st_attn_task(ph.at, act_smem, ring, full_bar, empty_bar, (uint32_t)(args.n_slots / ST_W), seq, ag, task / n_cg, task % n_cg, pick_v, red);
+          seq += (uint32_t)(ag.n_k + ag.n_v);
+        }
+      } else {
+        for (int task = blockIdx.x; task < n_tasks; task += G) {
+          if (task != (int)blockIdx.x) bar_sync<ST_BAR, ST_NT>();
+          attn_body<ST_NT, ST_BAR, false>(ph.at, act_smem, task / n_cg, 0, task % n_cg, ph.at.state);
+        }
       }
     } else if (ph.kind == PH_EMBED) {
       if (blockIdx.x == 0) {
@@ -977,8 +1013,8 @@ inline StepLaunch step_launch_shape(const Phase* phases, int n, int n_sm, size_t
   act = (act + 127) & ~(size_t)127;
   StepLaunch L;
   L.grid = n_sm;
-  if (act + 2 * (size_t)ST_SLOT > max_dyn_smem) { L.n_slots = 0; L.smem = 0; return L; }
-  L.n_slots = (int)std::min<size_t>(ST_MAX_SLOTS, (max_dyn_smem - act) / ST_SLOT);
+  if (act + (size_t)ST_W * ST_SLOT > max_dyn_smem) { L.n_slots = 0; L.smem = 0; return L; }
+  L.n_slots = ST_W * (int)std::min<size_t>(ST_MAX_DEPTH, (max_dyn_smem - act) / ((size_t)ST_W * ST_SLOT));   // whole sub-rings only
   L.smem = (size_t)L.n_slots * ST_SLOT + act;
   return L;
 }
@@ -990,6 +1026,14 @@ inline std::vector<int> step_bounds(const MVParams& p, int grid) {
   std::vector<int> b((size_t)grid + 1);
   for (int c = 0; c <= grid; c++) b[c] = ts.boundary(c, grid);
   return b;
+}
+
+// can the attention phases of a model with this context feed K / V through a ring of n_slots slots?  A task holds all its V
+// items until it ends (its K items are released one by one), so they must fit beside a couple of slots of slack.
+inline bool st_attn_ring_ok(int n_ctx, int n_slots) {
+  const int nchv = (n_ctx + 255) / 256;
+  const int cv = std::max(1, std::min(8, ST_SLOT / (nchv * 512)));
+  return (ATTN_CH + cv - 1) / cv <= n_slots;
 }
 
 // a mat-vec phase the step kernel can run: all matrices K-quant (→ Q8_K activations), K a multiple of 256

@@ -7,7 +7,7 @@ import pytest
 
 Q4_K, Q5_K, Q6_K = 12, 13, 14
 COST = {Q4_K: 72, Q5_K: 88, Q6_K: 105}     # relative cost of a tile = bytes per row-block / 2
-CHUNK = {Q4_K: 4, Q5_K: 3, Q6_K: 3}        # blocks per work item (one ring slot)
+CHUNK = {Q4_K: 4, Q5_K: 3, Q6_K: 2}        # blocks per work item (one ring slot)
 BLOCK_BYTES = {Q4_K: 144, Q5_K: 176, Q6_K: 210}
 
 SHAPES = [
