@@ -107,7 +107,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
   total += 4 * (2 * (size_t)hp.n_embd + qkv + 4 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + 2 * (size_t)hp.n_vocab) + 64 * 256 + 8192;
-  total += ((size_t)hp.n_layer * 8 + 8) * (sizeof(Phase) * 2 + 1024) + 4096;   // the step programs and their per-CTA tile ranges
+  total += ((size_t)hp.n_layer * 8 + 8) * (sizeof(Phase) * 2 + 2 * 1024) + 8192;   // the step programs and their per-CTA tile ranges
   total += 1 << 20;
   return total;
 }
@@ -579,14 +579,6 @@ void Engine::build_ops() {
     op.ph.pk.logits = d_logits_; op.ph.pk.state = d_state_; op.ph.pk.out_tokens = nullptr; op.ph.pk.n = hp_.n_vocab;   // out_tokens: set in build_graphs
     ops_.push_back(op);
   }
-  // ---- per-CTA tile ranges of every step-kernel mat-vec, computed once
-  for (StepOp& op : ops_) {
-    if (op.ph.kind != PH_MATVEC || !op.stream) continue;
-    const std::vector<int> b = step_bounds(op.ph.mv, sm_count_);
-    int* d = (int*)alloc(b.size() * 4);
-    CTB_CUDA(cudaMemcpy(d, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
-    op.ph.bounds = d;
-  }
   // ---- the step kernel's shared-memory shape: ring slots fill what the largest activation image leaves
   bool any_stream = false;
   for (const StepOp& op : ops_) any_stream |= op.ph.kind == PH_MATVEC && op.stream;
@@ -605,18 +597,24 @@ void Engine::build_ops() {
   else fused_ = false;
   d_prog_ = (Phase*)alloc((ops_.size() + 1) * sizeof(Phase), 256);
   d_prog_mv_ = (Phase*)alloc((ops_.size() + 1) * sizeof(Phase), 256);
+  d_bounds_ = (int*)alloc((ops_.size() + 1) * (size_t)(sm_count_ + 1) * 4, 256);      // per-CTA tile ranges, one row per phase
+  d_bounds_mv_ = (int*)alloc((ops_.size() + 1) * (size_t)(sm_count_ + 1) * 4, 256);
 }
 
-void Engine::upload_prog(Phase* dst, const std::vector<StepOp>& ops) {
+void Engine::upload_prog(Phase* dst, int* dst_bounds, const std::vector<StepOp>& ops) {
   std::vector<Phase> phs(ops.size());
   for (size_t i = 0; i < ops.size(); i++) phs[i] = ops[i].ph;
   CTB_CUDA(cudaMemcpy(dst, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));
+  std::vector<Phase> run = phs;
+  for (size_t i = 0; i < ops.size(); i++) if (ops[i].ph.kind == PH_MATVEC && !ops[i].stream) run[i].kind = -1;   // not a step-kernel phase
+  const std::vector<int> b = step_bounds(run.data(), (int)run.size(), sm_count_);
+  CTB_CUDA(cudaMemcpy(dst_bounds, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
 }
 
 // Enqueue ops[0, n) on stream_.  Fused mode: maximal runs of ops the step kernel can take become ONE k_step launch (a
 // K-quant model: the whole token); anything else (Q4_0 / Q8_0 / F16 / F32 mat-vecs) runs as its own kernel.  Un-fused mode
 // (CTB_STEP_FUSE=0): one kernel per op, K-quant mat-vecs as one-phase k_step launches.
-void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n) {
+void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, const int* d_bounds, int n) {
   launches_per_step_ = 0;
   StepLaunch step_shape_;
   step_shape_.grid = step_grid_; step_shape_.n_slots = step_slots_; step_shape_.smem = step_smem_;
@@ -628,7 +626,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, in
       int j = i;
       while (j < n && capable(ops[j])) j++;
       mark(-1);
-      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, j - i, d_sync_));
+      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, d_bounds + (size_t)i * (sm_count_ + 1), j - i, d_sync_));
       launches_per_step_++;
       mark(0);
       i = j;
@@ -661,7 +659,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, in
         break;
       default:
         if (op.stream) {
-          CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, 1, d_sync_));
+          CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, d_bounds + (size_t)i * (sm_count_ + 1), 1, d_sync_));
         } else {
           const MVLaunch L = matvec_launch_shape(op.ph.mv, sm_count_);
           CTB_CUDA(launch_matvec_kernel(L, stream_, op.ph.mv, pdl_));
@@ -693,7 +691,7 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
   const long keep = launches_per_step_;
   const bool keep_fused = fused_;
   profiling_ = true; fused_ = false;
-  try { enqueue_ops(ops_, d_prog_, n_body_ + 1); } catch (...) { profiling_ = false; fused_ = keep_fused; throw; }
+  try { enqueue_ops(ops_, d_prog_, d_bounds_, n_body_ + 1); } catch (...) { profiling_ = false; fused_ = keep_fused; throw; }
   profiling_ = false; fused_ = keep_fused;
   launches_per_step_ = keep;
   CTB_CUDA(cudaStreamSynchronize(stream_));
@@ -720,7 +718,7 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   for (int i = 0; i <= n_body_; i++)
     if (ops_[i].ph.kind == PH_MATVEC && ((mask >> ops_[i].mvk) & 1)) sel.push_back(ops_[i]);
   if (sel.empty()) { if (launches) *launches = 0; return 0.0; }
-  upload_prog(d_prog_mv_, sel);
+  upload_prog(d_prog_mv_, d_bounds_mv_, sel);
   cudaStream_t user = stream_, cap;
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   const long keep = launches_per_step_;
@@ -729,7 +727,7 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   try {
     cudaGraph_t g;
     CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_ops(sel, d_prog_mv_, (int)sel.size());
+    enqueue_ops(sel, d_prog_mv_, d_bounds_mv_, (int)sel.size());
     CTB_CUDA(cudaStreamEndCapture(cap, &g));
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
     cudaGraphDestroy(g);
@@ -751,29 +749,29 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
 }
 
 // One fused decode step with the step kernel stamping %globaltimer per phase and CTA (4 stamps: barrier passed, input staged,
-// first weight item ready, phase done).  out: n_phases x {kind, mvk} then n_phases x n_cta x 4 stamps; returns n_phases or -(words needed).
+// first weight item ready, phase done + 4 stamps of the grid barrier in front of the phase).  out: n_phases x {kind, mvk} then n_phases x n_cta x 8 stamps; returns n_phases or -(words needed).
 long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
   DeviceGuard dev_guard(device_);
   spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
   const int n = n_body_ + 1;
   for (int i = 0; i < n; i++)
     if (ops_[i].ph.kind == PH_MATVEC && !ops_[i].stream) return 0;
-  const long need = 2L * n + 4L * n * step_grid_;
+  const long need = 2L * n + 8L * n * step_grid_;
   if (need > cap_words) return -need;
   unsigned long long* buf = nullptr;
-  CTB_CUDA(cudaMalloc(&buf, (size_t)n * step_grid_ * 32));
-  CTB_CUDA(cudaMemset(buf, 0, (size_t)n * step_grid_ * 32));
+  CTB_CUDA(cudaMalloc(&buf, (size_t)n * step_grid_ * 64));
+  CTB_CUDA(cudaMemset(buf, 0, (size_t)n * step_grid_ * 64));
   StepLaunch L;
   L.grid = step_grid_; L.n_slots = step_slots_; L.smem = step_smem_;
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   for (int rep = 0; rep < 3; rep++) {   // the last (warm) run is the one read back
     h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
     CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
-    CTB_CUDA(launch_step(L, stream_, d_prog_, n, d_sync_, false, buf));
+    CTB_CUDA(launch_step(L, stream_, d_prog_, d_bounds_, n, d_sync_, false, buf));
     CTB_CUDA(cudaStreamSynchronize(stream_));
   }
   for (int i = 0; i < n; i++) { out[2 * i] = (unsigned long long)ops_[i].ph.kind; out[2 * i + 1] = (unsigned long long)ops_[i].mvk; }
-  const cudaError_t e = cudaMemcpy(out + 2 * n, buf, (size_t)n * step_grid_ * 32, cudaMemcpyDeviceToHost);
+  const cudaError_t e = cudaMemcpy(out + 2 * n, buf, (size_t)n * step_grid_ * 64, cudaMemcpyDeviceToHost);
   cudaFree(buf);
   CTB_CUDA(e);
   return n;
@@ -798,11 +796,11 @@ void Engine::build_graphs() {
   CTB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
   stream_ = cap;
   ops_.back().ph.pk.out_tokens = d_tokens_out_;
-  upload_prog(d_prog_, ops_);
+  upload_prog(d_prog_, d_bounds_, ops_);
   auto capture = [&](bool logits, bool greedy) {
     cudaGraph_t g;
     CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_ops(ops_, d_prog_, n_body_ + (logits ? 1 : 0) + (greedy ? 1 : 0));
+    enqueue_ops(ops_, d_prog_, d_bounds_, n_body_ + (logits ? 1 : 0) + (greedy ? 1 : 0));
     CTB_CUDA(cudaStreamEndCapture(cap, &g));
     cudaGraphExec_t ex;
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));
@@ -1062,7 +1060,7 @@ void Engine::prefill_batch(const int* tokens, const int* pos, const int* n_total
     fused_ = false;                                    // just this one op, the way the un-fused schedule launches it
     std::vector<StepOp> one(1, head);
     const long keepl = launches_per_step_;
-    try { enqueue_ops(one, d_prog_ + n_body_, 1); } catch (...) { fused_ = keep; throw; }
+    try { enqueue_ops(one, d_prog_ + n_body_, d_bounds_ + (size_t)n_body_ * (sm_count_ + 1), 1); } catch (...) { fused_ = keep; throw; }
     fused_ = keep;
     launches_per_step_ = keepl;
   }

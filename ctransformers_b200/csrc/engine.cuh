@@ -130,14 +130,15 @@ class Engine {
   int n_body_ = 0;               // ops before the HEAD mat-vec
   Phase* d_prog_ = nullptr;      // device copy of ops_' phases (index = op index)
   Phase* d_prog_mv_ = nullptr;   // scratch program of time_matvec_only
+  int *d_bounds_ = nullptr, *d_bounds_mv_ = nullptr;   // per-CTA tile ranges of the two programs
   unsigned* d_sync_ = nullptr;   // grid-barrier words of the step kernel
   int step_grid_ = 0, step_slots_ = 0;   // launch shape of the step kernel: CTAs, ring slots,
   size_t step_smem_ = 0;                 // dynamic shared memory
   bool fused_ = true;            // CTB_STEP_FUSE=0: one kernel per op
   void build_ops();
   void push_matvec(struct MVParams& p, int kind);
-  void upload_prog(Phase* dst, const std::vector<StepOp>& ops);
-  void enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, int n);
+  void upload_prog(Phase* dst, int* dst_bounds, const std::vector<StepOp>& ops);
+  void enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, const int* d_bounds, int n);
   void build_graphs();
   void destroy_graphs();
   bool eager_ = false;           // host logits / embeddings are refreshed by every eval

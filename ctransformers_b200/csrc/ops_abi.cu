@@ -111,19 +111,14 @@ void run_phases(std::vector<Phase> phs) {
   static unsigned* d_sync = nullptr;
   if (!d_sync) { OPS_CUDA(cudaMalloc((void**)&d_sync, 64)); OPS_CUDA(cudaMemset(d_sync, 0, 64)); }
   const StepLaunch L = step_launch_shape(phs.data(), (int)phs.size(), sm_count(), step_max_dyn_smem());
-  std::vector<std::unique_ptr<DevBuf>> bounds;
-  for (Phase& ph : phs) {
-    if (ph.kind != PH_MATVEC) continue;
-    const std::vector<int> b = step_bounds(ph.mv, L.grid);
-    bounds.emplace_back(new DevBuf(b.size() * 4));
-    OPS_CUDA(cudaMemcpy(bounds.back()->p, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
-    ph.bounds = bounds.back()->as<int>();
-  }
+  const std::vector<int> hb = step_bounds(phs.data(), (int)phs.size(), L.grid);
+  DevBuf dbounds(hb.size() * 4);
+  OPS_CUDA(cudaMemcpy(dbounds.p, hb.data(), hb.size() * 4, cudaMemcpyHostToDevice));
   if (L.n_slots < ST_W) throw std::runtime_error("rows too long for the step kernel's shared memory");
   OPS_CUDA(step_set_smem_limit(L.smem));
   DevBuf dprog((phs.size() + 1) * sizeof(Phase));
   OPS_CUDA(cudaMemcpy(dprog.p, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));
-  OPS_CUDA(launch_step(L, 0, dprog.as<Phase>(), (int)phs.size(), d_sync));
+  OPS_CUDA(launch_step(L, 0, dprog.as<Phase>(), dbounds.as<int>(), (int)phs.size(), d_sync));
   OPS_CUDA(cudaGetLastError());
   OPS_CUDA(cudaDeviceSynchronize());
 }

@@ -168,9 +168,10 @@ struct StAct {
   const float* d;
   const uint32_t* pairs;
   const int* cneg;
+  const int8_t* zero;   // 256 zero bytes (what the off-diagonal lanes of the mma B operand read)
 };
 __host__ __device__ inline size_t st_off_pairs(int K) { return ((((size_t)K + 15) & ~(size_t)15) + q8k_d_bytes(K) + (size_t)(K / 16) * 2 + 15) & ~(size_t)15; }
-__host__ __device__ inline size_t st_act_bytes(int K, bool q6) { return st_off_pairs(K) + (size_t)(K / 256) * 16 + (q6 ? (size_t)K : 0) + 16; }
+__host__ __device__ inline size_t st_act_bytes(int K, bool q6) { return st_off_pairs(K) + (size_t)(K / 256) * 16 + (q6 ? (size_t)K : 0) + 256 + 16; }
 
 template <int NT, int BAR>
 __device__ __forceinline__ StAct st_act_extras(uint8_t* smem, int K, bool q6) {
@@ -181,6 +182,9 @@ __device__ __forceinline__ StAct st_act_extras(uint8_t* smem, int K, bool q6) {
   int* cneg = (int*)(smem + st_off_pairs(K) + (size_t)(K / 256) * 16);
   s.pairs = pairs; s.cneg = cneg;
   const int nb = K >> 8;
+  int* zero = (int*)(smem + st_off_pairs(K) + (size_t)nb * 16 + (q6 ? (size_t)K : 0));
+  s.zero = (const int8_t*)zero;
+  if (threadIdx.x < 64) zero[threadIdx.x] = 0;
   for (int i = threadIdx.x; i < nb * 4; i += NT) {
     const int16_t* b4 = a.bs + (i >> 2) * 16 + 4 * (i & 3);
     const int p0 = (int)b4[0] + (int)b4[1], p1 = (int)b4[2] + (int)b4[3];
@@ -221,15 +225,13 @@ struct Terms { float p[4]; float pm[2]; float dd[2]; float ddm[2]; };
 
 __device__ __forceinline__ void load_b_operands(const StAct& a, int b, int g, int t, uint32_t (&bA)[8], uint32_t (&bB)[8]) {
   // block-diagonal B: thread (g, t) holds rows 4t..4t+3 / 16+4t.. of column g, which are non-zero only for g == t / g == t+4.
-  // Branch-free (every lane loads, the off-diagonal lanes select zero) so that ptxas can interleave the blocks of an item.
-  const int l = g & 3;   // the AVX lane whose words this thread would need: l = t for the diagonal lanes, l + 4 for the second half
-  const int4 lo = *(const int4*)(a.qs + b * 256 + g * 16), hi = *(const int4*)(a.qs + b * 256 + 128 + g * 16);
-  const uint32_t mA = (g == t) ? 0xffffffffu : 0u, mB = (g == t + 4) ? 0xffffffffu : 0u;
-  (void)l;
-  bA[0] = (uint32_t)lo.x & mA; bA[1] = (uint32_t)lo.y & mA; bA[2] = (uint32_t)lo.z & mA; bA[3] = (uint32_t)lo.w & mA;
-  bA[4] = (uint32_t)hi.x & mA; bA[5] = (uint32_t)hi.y & mA; bA[6] = (uint32_t)hi.z & mA; bA[7] = (uint32_t)hi.w & mA;
-  bB[0] = (uint32_t)lo.x & mB; bB[1] = (uint32_t)lo.y & mB; bB[2] = (uint32_t)lo.z & mB; bB[3] = (uint32_t)lo.w & mB;
-  bB[4] = (uint32_t)hi.x & mB; bB[5] = (uint32_t)hi.y & mB; bB[6] = (uint32_t)hi.z & mB; bB[7] = (uint32_t)hi.w & mB;
+  // Branch-free (ptxas interleaves the blocks of an item): the off-diagonal lanes load from a run of zero bytes instead.
+  const int8_t* word = a.qs + b * 256 + g * 16;
+  const int8_t* pa = (g == t) ? word : a.zero;
+  const int8_t* pb = (g == t + 4) ? word : a.zero;
+  const int4 la = *(const int4*)pa, ha = *(const int4*)(pa + 128), lb = *(const int4*)pb, hb = *(const int4*)(pb + 128);
+  bA[0] = la.x; bA[1] = la.y; bA[2] = la.z; bA[3] = la.w; bA[4] = ha.x; bA[5] = ha.y; bA[6] = ha.z; bA[7] = ha.w;
+  bB[0] = lb.x; bB[1] = lb.y; bB[2] = lb.z; bB[3] = lb.w; bB[4] = hb.x; bB[5] = hb.y; bB[6] = hb.z; bB[7] = hb.w;
 }
 
 template <int TYPE>
@@ -510,7 +512,6 @@ struct alignas(16) Phase {
   int kind;
   int q6;           // PH_MATVEC: some matrix of the phase is Q6_K (the activation staging then also builds cneg)
                     // PH_ATTN: 1 = cached K / V travel through the ring (st_attn_ring_ok), 0 = read from global memory (attn_body)
-  const int* bounds;   // PH_MATVEC: [grid + 1] first tile of every CTA (TileSpace::boundary, computed once on the host: step_bounds)
   MVParams mv;      // PH_MATVEC
   AttnParams at;    // PH_ATTN
   EmbedParams em;   // PH_EMBED
@@ -522,7 +523,9 @@ struct StepArgs {
   int n_phases;
   int n_slots;
   unsigned* sync;   // [0] grid-barrier arrivals, [1] finished CTAs (the last one resets both)
-  unsigned long long* trace;   // optional: per phase and CTA 4 globaltimer stamps {barrier passed, input staged, first item ready, phase done}
+  const int* bounds;   // [n_phases][grid + 1]: first tile of every CTA per mat-vec phase (TileSpace::boundary, computed once on the host)
+  unsigned long long* trace;   // optional: per phase and CTA 8 globaltimer stamps {phase starts, input staged, first item ready, phase done,
+                               //           previous phase left (barrier entered), arrive issued, all arrived seen, acquire fence done}
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
@@ -778,7 +781,8 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
     const MVParams& p = ph->mv;
     TileSpace ts;
     ts.init(p);
-    const int T0 = __ldg(ph->bounds + blockIdx.x), T1 = __ldg(ph->bounds + blockIdx.x + 1);
+    const int* bnd = args.bounds + (size_t)ip * (gridDim.x + 1) + blockIdx.x;
+    const int T0 = __ldg(bnd), T1 = __ldg(bnd + 1);
     const int nb = p.K >> 8;
     for (int w0 = T0; w0 < T1; w0 += ST_MAXT) {
       const int ntw = min(ST_MAXT, T1 - w0);
@@ -928,33 +932,38 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     const uint32_t dst = st_smem(&ph_s[ip & 1]);
     const int i = (int)threadIdx.x - 32;
     if (i >= 0 && i < (int)(sizeof(Phase) / 16)) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+    if (i >= 64 && i < 66)   // this CTA's tile range of that phase
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(st_smem(&tb_s[ip & 1][i - 64])), "l"(args.bounds + (size_t)ip * (gridDim.x + 1) + blockIdx.x + (i - 64)) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   fetch_phase(0);
 #pragma unroll 1
   for (int ip = 0; ip < args.n_phases; ip++) {
     bar_sync<ST_BAR, ST_NT>();                 // every consumer warp is done with the previous phase (its stores are issued)
-    if (threadIdx.x == 0 && ip > 0) {          // grid barrier: one release-arrive, relaxed polls, one acquire fence at the end
+    unsigned long long* const tr = args.trace ? args.trace + ((size_t)ip * G + blockIdx.x) * 8 : nullptr;
+    if (tr && threadIdx.x == 0) tr[4] = globaltimer_ns();
+    if (threadIdx.x == 0 && ip > 0) {          // grid barrier: one release-arrive, then relaxed polls
       const unsigned target = (unsigned)ip * G;
       asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(args.sync) : "memory");
+      if (tr) tr[5] = globaltimer_ns();
       if (ld_relaxed_u32(args.sync) < target) {
         const unsigned long long t0 = globaltimer_ns();
         while (ld_relaxed_u32(args.sync) < target) {
           if (globaltimer_ns() - t0 > ST_WATCHDOG_NS) st_fail(2, ip);
         }
       }
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      if (tr) { tr[6] = globaltimer_ns(); tr[7] = tr[6]; }
+      // no acquire fence: everything the other CTAs produced is read with ld.global.cg (L2, never a stale L1 line), and those
+      // loads are issued after the CTA barrier below, i.e. after this poll has returned
     } else {
       asm volatile("cp.async.wait_all;" ::: "memory");
       if (threadIdx.x >= 32 && threadIdx.x < 32 + ST_MAXT) flags[threadIdx.x - 32] = 0;   // (thread 0 is busy with the grid barrier)
     }
     bar_sync<ST_BAR, ST_NT>();
     const Phase& ph = ph_s[ip & 1];
-    if (ph.kind == PH_MATVEC && threadIdx.x < 2) tb_s[ip & 1][threadIdx.x] = __ldg(ph.bounds + blockIdx.x + threadIdx.x);
     fetch_phase(ip + 1);
     NormPre np;
     if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);
-    unsigned long long* const tr = args.trace ? args.trace + ((size_t)ip * G + blockIdx.x) * 4 : nullptr;
     if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
     if (ph.kind == PH_MATVEC) {
       // (the tile bounds were written by threads 0/1 above; the barriers inside the activation staging order them)
@@ -1019,12 +1028,15 @@ inline StepLaunch step_launch_shape(const Phase* phases, int n, int n_sm, size_t
   return L;
 }
 
-// first tile of every CTA of a mat-vec phase (the device reads it from Phase::bounds instead of redoing the 64-bit divisions)
-inline std::vector<int> step_bounds(const MVParams& p, int grid) {
-  TileSpace ts;
-  ts.init(p);
-  std::vector<int> b((size_t)grid + 1);
-  for (int c = 0; c <= grid; c++) b[c] = ts.boundary(c, grid);
+// first tile of every CTA for every phase of a program, [n][grid + 1] (the device reads it instead of redoing the 64-bit divisions)
+inline std::vector<int> step_bounds(const Phase* phs, int n, int grid) {
+  std::vector<int> b((size_t)n * (grid + 1), 0);
+  for (int i = 0; i < n; i++) {
+    if (phs[i].kind != PH_MATVEC) continue;
+    TileSpace ts;
+    ts.init(phs[i].mv);
+    for (int c = 0; c <= grid; c++) b[(size_t)i * (grid + 1) + c] = ts.boundary(c, grid);
+  }
   return b;
 }
 
@@ -1064,10 +1076,10 @@ static inline size_t step_max_dyn_smem() {
 static inline cudaError_t st_set_debug_words(int* dev_ptr) { return cudaMemcpyToSymbol(g_st_dbg, &dev_ptr, sizeof(int*)); }
 static inline cudaError_t step_set_smem_limit(size_t bytes) { return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
 
-static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, int n_phases, unsigned* d_sync, bool pdl = false,
+static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, const int* d_bounds, int n_phases, unsigned* d_sync, bool pdl = false,
                                       unsigned long long* trace = nullptr) {
   StepArgs a;
-  a.prog = d_prog; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync; a.trace = trace;
+  a.prog = d_prog; a.bounds = d_bounds; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync; a.trace = trace;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(L.grid); cfg.blockDim = dim3(ST_THREADS); cfg.dynamicSmemBytes = L.smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
