@@ -40,7 +40,10 @@ constexpr int ST_W = CTB_ST_WARPS;      // consumer warps
 constexpr int ST_NT = ST_W * 32;        // consumer threads (threads 0 .. ST_NT-1)
 constexpr int ST_THREADS = ST_NT + 32;  // + the producer warp
 constexpr int ST_SLOT = 9216;           // ring slot: holds 4 Q4_K / 3 Q5_K / 2 Q6_K blocks of a 16-row tile
-constexpr int ST_MAX_DEPTH = 2;         // slots per consumer warp; the ring has ST_W * depth slots
+#ifndef CTB_ST_DEPTH
+#define CTB_ST_DEPTH 2
+#endif
+constexpr int ST_MAX_DEPTH = CTB_ST_DEPTH;   // slots per consumer warp; the ring has ST_W * depth slots
 constexpr int ST_MAX_SLOTS = ST_W * ST_MAX_DEPTH;
 constexpr int ST_MAXT = 16;             // tiles of a CTA whose fold chains are alive at the same time (one mailbox each)
 constexpr int ST_ROWS = 16;

@@ -1,122 +1,107 @@
 #!/usr/bin/env python
-"""Turn one round's gpurun_out/<tag>/ captures into the tracked summaries under profiles/.
+"""Turn a round's gpurun_out/ captures into the tracked summaries under profiles/.
 
-    python tools/make_profiles.py r01
+    python tools/make_profiles.py r02 gpurun_out/r02_full.ncu-rep
 
 Inputs (written on the GPU box by the commands quoted in profiles/<tag>_README.md):
-  bench_n1.json, bench_reference.json   bench.py lines (not under a profiler)
-  launches_step.csv                     ncu --metrics gpu__time_duration.sum,dram__bytes_* ... of one whole decode step
-  prof_full.ncu-rep                     ncu --set full --import-source on of the first kernels of a decode step
+  <report>.ncu-rep      ncu --set full --import-source on of k_pstep / k_step launches of tools/prof_decode.py
+Outputs: profiles/<tag>_ncu_metrics.csv (one row per captured launch), profiles/<tag>_ncu_stalls.md (stall mix, opcode mix and the
+hottest SASS lines per kernel), profiles/<tag>_sass_evidence.txt (the TMA / mbarrier / tensor-core instructions of the step kernel),
+profiles/k_step_traffic.json (DRAM bytes of the decode launch: bench.py's roofline.traffic).
 """
+import collections
 import csv
 import json
-import shutil
+import re
 import subprocess
 import sys
-from collections import OrderedDict, defaultdict
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-src = ROOT / "gpurun_out" / tag
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+rep = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "gpurun_out" / f"{tag}_full.ncu-rep"
 out = ROOT / "profiles"
 out.mkdir(exist_ok=True)
 
-for name in ("bench_n1.json", "bench_reference.json", "smi.csv", "host.txt"):
-    if (src / name).exists():
-        shutil.copy(src / name, out / f"{tag}_{name}")
 
-# ---- launch list of one decode step
-rows = list(csv.reader(open(src / "launches_step.csv")))
-h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-H = rows[h]
-ki, gi, bi = H.index("Kernel Name"), H.index("Grid Size"), H.index("Block Size")
-launches = OrderedDict()
-for r in rows[h + 1:]:
-    if len(r) < len(H) or not r[0].isdigit():
-        continue
-    d = launches.setdefault(int(r[0]), {"kernel": r[ki], "grid": r[gi], "block": r[bi]})
-    d[r[-3]] = float(r[-1].replace(",", ""))
-short = lambda k: k.split("(")[0].replace("void ", "").replace("ctb::", "")
-with open(out / f"{tag}_launches_step.csv", "w", newline="") as f:
+def ncu(*args):
+    return subprocess.run(["ncu", "-i", str(rep), *args], capture_output=True, text=True, check=True).stdout
+
+
+# ---- raw metrics, one row per launch
+rows = list(csv.reader(ncu("--page", "raw", "--csv").splitlines()))
+H, U = rows[0], rows[1]
+KEEP = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "sm__cycles_elapsed.max"] + [h for h in H if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+idx = [H.index(k) for k in KEEP if k in H]
+with open(out / f"{tag}_ncu_metrics.csv", "w", newline="") as f:
     w = csv.writer(f)
-    w.writerow(["id", "kernel", "grid", "time_us", "dram_read_MB", "dram_write_MB", "warp_inst", "issue_active_pct"])
-    for i, d in launches.items():
-        w.writerow([i, short(d["kernel"]), d["grid"], round(d.get("gpu__time_duration.sum", 0) / 1e3, 3), round(d.get("dram__bytes_read.sum", 0) / 1e6, 3),
-                    round(d.get("dram__bytes_write.sum", 0) / 1e6, 3), int(d.get("smsp__inst_executed.sum", 0)), d.get("smsp__issue_active.avg.pct_of_peak_sustained_active")])
-agg = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-for d in launches.values():
-    k = "k_matvec" if "k_matvec" in d["kernel"] else short(d["kernel"])
-    a = agg[k]
-    a[0] += 1; a[1] += d.get("gpu__time_duration.sum", 0) / 1e3; a[2] += d.get("dram__bytes_read.sum", 0); a[3] += d.get("dram__bytes_write.sum", 0)
-total_us = sum(a[1] for a in agg.values())
-mv = agg["k_matvec"]
-traffic = {"source": f"profiles/{tag}_launches_step.csv (ncu dram__bytes_read.sum + dram__bytes_write.sum, one decode step, per launch)",
-           "launches": mv[0], "dram_bytes_per_step": mv[2] + mv[3], "dram_bytes_per_launch_avg": (mv[2] + mv[3]) / max(1, mv[0])}
-(out / "k_matvec_traffic.json").write_text(json.dumps(traffic, indent=1) + "\n")
+    w.writerow([H[i] for i in idx])
+    w.writerow([U[i] for i in idx])
+    for r in rows[2:]:
+        w.writerow([r[i] for i in idx])
 
-bench = json.loads((src / "bench_n1.json").read_text()) if (src / "bench_n1.json").exists() else {}
-ref = json.loads((src / "bench_reference.json").read_text()) if (src / "bench_reference.json").exists() else {}
-md = [f"# {tag}: one decode step of the bench workload under ncu (cold caches, serialised launches, no PDL overlap)", "",
-      "| kernel | launches | sum of launch times (us) | share | dram read (MB) | dram write (MB) |", "|---|---|---|---|---|---|"]
-for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    md.append(f"| {k} | {a[0]} | {a[1]:.1f} | {100 * a[1] / total_us:.1f} % | {a[2] / 1e6:.1f} | {a[3] / 1e6:.2f} |")
-md += ["", f"Sum over the step: {total_us:.0f} us under ncu.  These per-launch times are cold-cache and serialised; only the SHARE is comparable with bench.py."]
-if bench:
-    r = bench["roofline"]
-    e = r["eager_ms_per_step_by_kind"]
-    tot = e["matvec"] + e["attention"] + e["other"]
-    md += ["", "## bench.py (same build, not under a profiler)", "",
-           f"* value {bench['value']:.1f} tokens/s ({bench['ms_per_step']:.4f} ms/step, device-timed graph replays), e2e {bench['e2e']['value']:.1f} tokens/s, clocks {bench['clocks']}",
-           f"* k_matvec roofline: {r['achieved']:.0f} GB/s of {r['peak']:.0f} GB/s = {100 * r['frac']:.1f} %  ({r['launches_per_step']} launches, {r['algorithmic_bytes_per_launch'] / 1e6:.2f} MB and {r['avg_launch_us']:.2f} us per launch on average; ncu traffic {traffic['dram_bytes_per_launch_avg'] / 1e6:.2f} MB per launch)",
-           f"* whole step: {r['step']['achieved']:.0f} GB/s = {100 * r['step']['frac']:.1f} % of peak",
-           f"* kernel share of the step, eager pass with an event after every kernel: matvec {100 * e['matvec'] / tot:.1f} %, attention {100 * e['attention'] / tot:.1f} %, other {100 * e['other'] / tot:.1f} %  (ncu share above: matvec {100 * mv[1] / total_us:.1f} %)"]
-    if "cpu_baseline" in bench:
-        md.append(f"* cpu_baseline: {bench['cpu_baseline']['value']:.2f} tokens/s — {bench['cpu_baseline']['sample']}")
-if ref:
-    md.append(f"* --impl reference: {ref['value']:.2f} tokens/s — {ref['cpu_baseline']['sample']}; thread sweep (s/token): {ref['cpu_baseline']['thread_sweep_s_per_token']}")
-(out / f"{tag}_step_summary.md").write_text("\n".join(md) + "\n")
+# the decode launch = the longest k_step launch captured
+ki, ti = H.index("Kernel Name"), H.index("gpu__time_duration.sum")
+step_rows = [r for r in rows[2:] if "k_step" in r[ki]]
+if step_rows:
+    dec = max(step_rows, key=lambda r: float(r[ti]))
+    rd, wr = float(dec[H.index("dram__bytes_read.sum")]), float(dec[H.index("dram__bytes_write.sum")])
+    unit_r, unit_w = U[H.index("dram__bytes_read.sum")], U[H.index("dram__bytes_write.sum")]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = rd * scale[unit_r] + wr * scale[unit_w]
+    (out / "k_step_traffic.json").write_text(json.dumps({
+        "source": f"profiles/{tag}_ncu_metrics.csv (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one whole decode launch of k_step: "
+                  "129 mat-vec phases + 32 attention phases + embedding + pick at a context of ~45)",
+        "dram_bytes_per_step": total, "matvec_phases": 129, "dram_bytes_per_matvec_phase_avg": total / 129,
+        "algorithmic_weight_bytes_per_step": 4005470208, "ratio": total / 4005470208}, indent=1) + "\n")
 
-# ---- full capture: key metrics per captured kernel + top stall lines of the source page
-rep = src / "prof_full.ncu-rep"
-if rep.exists():
-    raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines()))
-    Hh = rr[0]
-    keep = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-            "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-            "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__cycles_elapsed.max", "smsp__cycles_active.avg"]
-    keep += [c for c in Hh if c.startswith("smsp__average_warps_issue_stalled_") and c.endswith("_per_issue_active.ratio")]
-    idx = [Hh.index(c) for c in keep if c in Hh]
-    with open(out / f"{tag}_ncu_full_metrics.csv", "w", newline="") as f:
-        w = csv.writer(f)
-        w.writerow([Hh[i] for i in idx]); w.writerow([rr[1][i] for i in idx])
-        for r in rr[2:]:
-            w.writerow([r[i] for i in idx])
-    srcp = subprocess.run(["ncu", "-i", str(rep), "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    sr = list(csv.reader(srcp.splitlines()))
-    starts = [i for i, r in enumerate(sr) if r and r[0] == "Kernel Name"] + [len(sr)]
-    lines = [f"# {tag}: warp-stall sampling per kernel (ncu --set full --import-source on), top instructions by samples", ""]
-    seen = set()
-    for a, b in zip(starts[:-1], starts[1:]):
-        name = sr[a][1]
-        Hs = sr[a + 1]; ci = {c: i for i, c in enumerate(Hs)}
-        data = sr[a + 2:b]
-        tot = sum(int(r[ci["# Samples"]] or 0) for r in data)
-        inst = sum(int(r[ci["Instructions Executed"]] or 0) for r in data)
-        key = (name, tot, inst)
-        if key in seen:
-            continue
-        seen.add(key)
-        kinds = [c for c in Hs if c.startswith("stall_") and "Not Issued" not in c]
-        ag = {k: sum(int(r[ci[k]] or 0) for r in data) for k in kinds}
-        lines += [f"## {name}", f"samples {tot}, warp instructions {inst}, SASS lines {len(data)}", "",
-                  "stall mix: " + ", ".join(f"{k[6:]} {100 * v / max(1, tot):.1f}%" for k, v in sorted(ag.items(), key=lambda kv: -kv[1]) if v > 0.02 * tot), "",
-                  "| sass line | samples | long_sb | short_sb | wait | no_inst | instruction |", "|---|---|---|---|---|---|---|"]
-        top = sorted(range(len(data)), key=lambda i: -int(data[i][ci["# Samples"]] or 0))[:12]
-        for i in sorted(top):
-            r = data[i]
-            lines.append(f"| {i} | {r[ci['# Samples']]} | {r[ci['stall_long_sb']]} | {r[ci['stall_short_sb']]} | {r[ci['stall_wait']]} | {r[ci['stall_no_inst']]} | `{r[ci['Source']].strip()[:80]}` |")
-        lines.append("")
-    (out / f"{tag}_ncu_stalls.md").write_text("\n".join(lines) + "\n")
-print("profiles written:", sorted(p.name for p in out.iterdir()))
+# ---- per-kernel stall / opcode summaries from the source page
+txt = ncu("--page", "source", "--csv", "--print-source", "sass")
+blocks = re.split(r'(?m)^"Kernel Name",', txt)[1:]
+md = [f"# {tag}: warp-stall sampling and instruction mix per captured launch (ncu --set full --import-source on; tools/prof_decode.py 40 3)", ""]
+evidence = []
+best_i = 0.0
+seen = collections.Counter()
+for blk in blocks:
+    lines = blk.splitlines()
+    name = lines[0].strip('",')
+    rws = list(csv.reader(lines[1:]))
+    hdr, data = rws[0], [r for r in rws[1:] if len(r) == len(rws[0])]
+    ix = {h: i for i, h in enumerate(hdr)}
+    num = lambda x: float(x) if x not in ("", None) else 0.0
+    tot_i = sum(num(r[ix["Instructions Executed"]]) for r in data)
+    tot_s = sum(num(r[ix["# Samples"]]) for r in data)
+    seen[name] += 1
+    md += [f"## {name}  (capture {seen[name]}: {tot_i:.0f} warp instructions, {tot_s:.0f} samples, {len(data)} SASS lines)", ""]
+    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+    mix = sorted(((sum(num(r[ix[s]]) for r in data), s) for s in stalls), reverse=True)[:8]
+    md += ["stall mix: " + ", ".join(f"{s[6:]} {100 * v / max(tot_s, 1):.1f}%" for v, s in mix), ""]
+    byop = collections.Counter()
+    for r in data:
+        m = re.match(r"\s*(@!?U?P\d\s+)?([A-Z0-9_.]+)", r[ix["Source"]])
+        byop[(m.group(2).split(".")[0] if m else "?")] += num(r[ix["Instructions Executed"]])
+    md += ["opcode mix (executed warp instructions): " + ", ".join(f"{op} {100 * c / max(tot_i, 1):.1f}%" for op, c in byop.most_common(14)), ""]
+    md += ["| samples | executed | top stalls | instruction |", "|---|---|---|---|"]
+    for r in sorted(data, key=lambda r: -num(r[ix["# Samples"]]))[:14]:
+        st = sorted(((num(r[ix[s]]), s[6:]) for s in stalls if num(r[ix[s]]) > 0), reverse=True)[:2]
+        md.append(f"| {num(r[ix['# Samples']]):.0f} | {num(r[ix['Instructions Executed']]):.0f} | {', '.join(f'{n} {v:.0f}' for v, n in st)} | `{r[ix['Source']].strip()[:70]}` |")
+    md.append("")
+    if "k_step" in name and tot_i > best_i:   # the decode launch = the k_step capture with the most instructions
+        best_i = tot_i
+        evidence = []
+        for r in data:
+            s_ = r[ix["Source"]]
+            if re.search(r"UBLKCP|SYNCS|IMMA|UTMA|RED\.|LDGSTS|BAR\.SYNC", s_):
+                evidence.append(f"{r[ix['Address']][-6:]}  executed {num(r[ix['Instructions Executed']]):>10.0f}  {s_.strip()}")
+(out / f"{tag}_ncu_stalls.md").write_text("\n".join(md) + "\n")
+(out / f"{tag}_sass_evidence.txt").write_text(
+    "SASS of ctb::k_step (sm_100a) as profiled: the TMA bulk copies (UBLKCP = cp.async.bulk), mbarrier operations (SYNCS), the legacy-path int8\n"
+    "tensor-core instructions (IMMA.16832.U8.S8 = mma.sync.m16n8k32), the cp.async descriptor prefetch (LDGSTS), named barriers and the grid-barrier RED.\n\n"
+    + "\n".join(evidence) + "\n")
+print("wrote", [p.name for p in out.glob(f"{tag}_*")], "k_step_traffic.json")
