@@ -20,7 +20,7 @@
 //           32 tokens, keeps those accumulators in registers across the K loop, rebuilds its A digits once per block and
 //           re-uses them for the 4 token groups; the team combines through shared memory at the end of a tile
 //   KV      RoPE + fp16 store of K and V of all tokens (llama.cpp:2303-2335) — before any attention task reads the cache
-//   ATTN    attention of every (token, head): attention.cuh attn_body
+//   ATTN    attention of every (token, head), one WARP per task (pb_attn_warp_task: attn_body's arithmetic without its CTA barriers)
 #pragma once
 #include "stream.cuh"
 
@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t pb_qs_word(const uint8_t* blk, int l, int rr
 }
 
 template <int TYPE>
-__device__ __forceinline__ void pb_block(const uint8_t* blk, int b, const uint8_t* qbuf, int nb, int lane, int lp, PBState& st) {
+__device__ __forceinline__ void pb_block(const uint8_t* blk, int b, const uint8_t* qbuf, int nb, int lane, int lp, int ntg, PBState& st) {
   const int g = lane >> 2, t = lane & 3;
   const uint32_t* Bq = (const uint32_t*)qbuf;
   const uint32_t* pairs = (const uint32_t*)(qbuf + (size_t)nb * 8192);
@@ -172,6 +172,7 @@ __device__ __forceinline__ void pb_block(const uint8_t* blk, int b, const uint8_
   // ---- the four token groups
 #pragma unroll
   for (int tg = 0; tg < PB_TG; tg++) {
+    if (tg >= ntg) break;   // a short batch (the tail of a prompt) skips its empty token groups
     const uint4 bw = __ldg((const uint4*)(Bq + (size_t)(((b * PB_TG + tg) * 4 + lp) * 32 + lane) * 4));
     const float2 yd = __ldg((const float2*)(ydp + b * PB_T + tg * 8 + 2 * t));
     float dd[4], ddm[4];
@@ -225,10 +226,10 @@ __device__ __forceinline__ void pb_block(const uint8_t* blk, int b, const uint8_
 }
 
 template <int TYPE>
-__device__ __forceinline__ void pb_chunk(const uint8_t* slot, int nblk, int b0, const uint8_t* qbuf, int nb, int lane, int lp, PBState& st) {
+__device__ __forceinline__ void pb_chunk(const uint8_t* slot, int nblk, int b0, const uint8_t* qbuf, int nb, int lane, int lp, int ntg, PBState& st) {
   constexpr int BB = StTraits<TYPE>::BB;
 #pragma unroll 1
-  for (int i = 0; i < nblk; i++) pb_block<TYPE>(slot + i * BB, b0 + i, qbuf, nb, lane, lp, st);
+  for (int i = 0; i < nblk; i++) pb_block<TYPE>(slot + i * BB, b0 + i, qbuf, nb, lane, lp, ntg, st);
 }
 
 // end of a tile: the team's 4 warps publish their accumulators, then its 128 threads finish 16 rows x PB_T tokens:
@@ -341,9 +342,9 @@ __device__ __forceinline__ void pb_gemm_phase(const PPhase& ph, int n_tok, uint8
         const int b0 = kc * kb, nblk = min(kb, nb - b0);
         const uint8_t* sp = ring + (size_t)slot * ST_SLOT;
         mbar_wait(&full_bar[slot], (cnt / D) & 1u, 15, (int)cnt);
-        if (my_type == GT_Q4_K) pb_chunk<GT_Q4_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
-        else if (my_type == GT_Q6_K) pb_chunk<GT_Q6_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
-        else pb_chunk<GT_Q5_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, st);
+        if (my_type == GT_Q4_K) pb_chunk<GT_Q4_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, (n_tok + 7) >> 3, st);
+        else if (my_type == GT_Q6_K) pb_chunk<GT_Q6_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, (n_tok + 7) >> 3, st);
+        else pb_chunk<GT_Q5_K>(sp, nblk, b0, ph.qbuf, nb, lane, lp, (n_tok + 7) >> 3, st);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[slot]);   // 4 arrivals (the team's warps) free the slot
         cnt++;
@@ -378,6 +379,113 @@ __device__ __forceinline__ void pb_kv_phase(const PPhase& ph, int n_tok) {
     vd[(size_t)(2 * i) * cp] = f2h(__ldcg(vsrc + 2 * i));
     vd[(size_t)(2 * i + 1) * cp] = f2h(__ldcg(vsrc + 2 * i + 1));
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention of one (token, head) by ONE warp (the CTA-wide attn_body of the decode path is a latency chain per task; a prompt
+// batch has n_tok x n_head independent tasks, so here every warp takes its own).  Same arithmetic, same order as attn_body
+// (attention.cuh): f16 dots with lane L on elements L, L+32, ..., the 4x8 reduction tree, fp16-table softmax with an exact
+// fp64 sum, V·P through the 32 lanes plus the scalar tail of n_total.  K and V of every position — the token's own included —
+// come from the cache: the KV phase has stored the whole batch before any task starts.
+__host__ __device__ inline size_t pb_attn_warp_bytes(int n_ctx, int hd) { return (((size_t)kv_ctx_pad(n_ctx) * 6 + (size_t)hd * 2) + 15) & ~(size_t)15; }
+
+__device__ __forceinline__ void pb_attn_warp_task(const AttnParams& p, const int* st, int tok, int h, uint8_t* wsm) {
+  const int lane = threadIdx.x & 31;
+  const int hd = p.hd, per = hd >> 5;
+  const int pos = st[1];
+  if (pos >= p.n_ctx) return;
+  const int T = pos + 1;
+  const int n_total = max(T, min(st[3], p.n_ctx));
+  const int n_vec = n_total & ~31;
+  const int lim = min(T, n_vec);
+  const int group = p.n_head / p.n_kv, kvh = h / group;
+  const int cp = kv_ctx_pad(p.n_ctx);
+  float* sc = (float*)wsm;
+  uint16_t* p16 = (uint16_t*)(wsm + (size_t)cp * 4);
+  uint16_t* q16 = p16 + cp;
+  {  // RoPE of q (llama.cpp:2303-2309), f16, K-permuted order
+    const float* qv = p.q + (size_t)tok * p.q_stride + (size_t)h * hd;
+    for (int i = lane; i < hd / 2; i += 32) {
+      const float2 cs = p.rope[(size_t)pos * (hd / 2) + i];
+      const int i0 = p.neox ? i : 2 * i, i1 = p.neox ? i + hd / 2 : 2 * i + 1;
+      float o0, o1;
+      rope_pair(__ldcg(qv + i0), __ldcg(qv + i1), cs, p.neox, o0, o1);
+      q16[k_perm(i0, hd)] = f2h(o0); q16[k_perm(i1, hd)] = f2h(o1);
+    }
+  }
+  __syncwarp();
+  const uint16_t* krows = p.kc + k_row(kvh, 0, p.n_ctx, hd);
+  if (per == 4) {
+    const uint2 qq = *(const uint2*)(q16 + lane * 4);
+    const float q0 = h2f((uint16_t)(qq.x & 0xffff)), q1 = h2f((uint16_t)(qq.x >> 16)), q2 = h2f((uint16_t)(qq.y & 0xffff)), q3 = h2f((uint16_t)(qq.y >> 16));
+    for (int t0 = 0; t0 < T; t0 += 8) {
+      uint2 kk[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) kk[j] = *(const uint2*)(krows + (size_t)min(t0 + j, T - 1) * hd + lane * 4);
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float s = 0.f;
+        s = __fmaf_rn(h2f((uint16_t)(kk[j].x & 0xffff)), q0, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[j].x >> 16)), q1, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[j].y & 0xffff)), q2, s);
+        s = __fmaf_rn(h2f((uint16_t)(kk[j].y >> 16)), q3, s);
+        s = attn_reduce_f32x8(s);
+        if (lane == j && t0 + j < T) sc[t0 + j] = __fmul_rn(s, p.kq_scale);
+      }
+    }
+  } else {
+    for (int t = 0; t < T; t++) {
+      const uint16_t* kr = krows + (size_t)t * hd + lane * per;
+      float s = 0.f;
+      for (int e = 0; e < per; e++) s = __fmaf_rn(h2f(kr[e]), h2f(q16[lane * per + e]), s);
+      s = attn_reduce_f32x8(s);
+      if (lane == 0) sc[t] = __fmul_rn(s, p.kq_scale);
+    }
+  }
+  __syncwarp();
+  // soft_max (ggml.c:12047-12069)
+  float mx = -INFINITY;
+  for (int t = lane; t < T; t += 32) mx = fmaxf(mx, sc[t]);
+  mx = warp_max(mx);
+  double sum = 0.0;
+  for (int t = lane; t < T; t += 32) {
+    const float val = h2f(__ldg(p.exp_tab + f2h(__fsub_rn(sc[t], mx))));
+    sc[t] = val;
+    sum += (double)val;
+  }
+  sum = warp_sum(sum);
+  const float inv = (float)(1.0 / sum);
+  const int t_end = (T + 255) & ~255;
+  __syncwarp();
+  for (int t = lane; t < t_end; t += 32) p16[v_perm(t)] = t < T ? f2h(__fmul_rn(sc[t], inv)) : (uint16_t)0;
+  __syncwarp();
+  // V·P, every channel of the head
+  const int left = T - n_vec;                         // <= 31; <= 0 when the eval chunk extends past this token
+  const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
+  const uint16_t* vhead = p.vc + (size_t)kvh * hd * cp;
+  float* orow = p.out + (size_t)tok * p.n_head * hd + (size_t)h * hd;
+  for (int c = 0; c < hd; c++) {
+    const uint16_t* vrow = vhead + (size_t)c * cp;
+    float s = 0.f;
+    for (int ch = 0; ch * 256 < lim; ch++) {
+      const uint4 vv = *(const uint4*)(vrow + ch * 256 + lane * 8);
+      const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
+      const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w}, pw[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int t = ch * 256 + 32 * i + lane;
+        if (t < lim) s = __fmaf_rn(h2f((uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff)), h2f((uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff)), s);
+      }
+    }
+    s = attn_reduce_f32x8(s);
+    double sumf = (double)s;
+    if (left > 0) {
+      const float term = __fmul_rn(h2f(vrow[ch_left * 256 + lane * 8 + i_left]), h2f(p16[ch_left * 256 + lane * 8 + i_left]));
+      for (int l = 0; l < left; l++) sumf += (double)__shfl_sync(0xffffffffu, term, l);
+    }
+    if (lane == 0) orow[c] = (float)sumf;
+  }
+  __syncwarp();
 }
 
 static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_constant__ PStepArgs args) {
@@ -434,13 +542,11 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
     } else if (ph.kind == PP_KV) {
       pb_kv_phase(ph, n_tok);
     } else if (ph.kind == PP_ATTN) {
-      const int n_cg = ph.at.hd / ATTN_CH, per_tok = ph.at.n_head * n_cg, n_tasks = n_tok * per_tok;
-      bool first = true;
-      for (int task = blockIdx.x; task < n_tasks; task += G) {
-        if (!first) bar_sync<PB_BAR, PB_NT>();
-        first = false;
-        const int tok = task / per_tok, r = task % per_tok;
-        attn_body<PB_NT, PB_BAR, false>(ph.at, work, r / n_cg, tok, r % n_cg, ph.state + tok * 4);
+      const int n_tasks = n_tok * ph.at.n_head;
+      uint8_t* wsm = work + (size_t)warp * pb_attn_warp_bytes(ph.at.n_ctx, ph.at.hd);
+      for (int task = blockIdx.x * PB_W + warp; task < n_tasks; task += (int)G * PB_W) {
+        const int tok = task / ph.at.n_head;
+        pb_attn_warp_task(ph.at, ph.state + tok * 4, tok, task % ph.at.n_head, wsm);
       }
     } else if (ph.kind == PP_EMBED) {
       for (int tok = blockIdx.x; tok < n_tok; tok += G) {
@@ -466,7 +572,7 @@ static __global__ void __launch_bounds__(PB_THREADS, 1) k_pstep(const __grid_con
 // Host side
 inline size_t pb_work_bytes(int K_max, int n_ctx, int hd) {
   size_t w = std::max<size_t>((size_t)PB_TEAMS * PB_XCH, act_smem_bytes(ACT_Q8_K, K_max) + 64);
-  w = std::max(w, attn_smem_bytes(n_ctx, hd));
+  w = std::max(w, (size_t)PB_W * pb_attn_warp_bytes(n_ctx, hd));
   return (w + 127) & ~(size_t)127;
 }
 static inline size_t pstep_max_dyn_smem() {
