@@ -52,6 +52,10 @@ WORKLOADS = {
 # configs[2]: prompt ingestion of the same model (the batched kernel of csrc/prefill.cuh); a separate bench line, not the driver's
 WORKLOADS["prefill2048"] = dict(WORKLOADS["llama2-7b"], metric="prefill tokens/s Llama-2-7B Q4_K_M 2048-token prompt",
                                 dtype="int8 mma.sync (u8 scale digits x s8 Q8_K activations, exact int32), fp32 combine in the reference's order")
+# configs[4]: the 13B shape, tensor-sharded over the ranks (--mode tp); also runs on one GPU (world 1 = the plain engine)
+WORKLOADS["llama2-13b"] = dict(file="llama2-13b-shaped.Q4_K_M.synthetic.gguf", arch="llama", shape="LLAMA2_13B", ftype="Q4_K_M", lo=259,
+                               metric="decode tokens/s Llama-2-13B Q4_K_M b=1 tensor-sharded", dtype=WORKLOADS["llama2-7b"]["dtype"],
+                               name="Llama-2-13B-shaped Q4_K_M GGUF")
 WL = WORKLOADS["llama2-7b"]
 
 
@@ -249,6 +253,76 @@ def run_prefill(args, path, rank, world, local, barrier, max_over_ranks, group):
     group.close()
 
 
+def run_tp(args, path, rank, world, local, barrier, max_over_ranks, group):
+    """configs[4]: ONE sequence decoded by all ranks together (strong scaling): every rank holds its heads / n_ff slice of the
+    layer weights, two NCCL all-reduces of n_embd floats per layer inside the step's CUDA graph (csrc/engine.cu build_ops)."""
+    import torch
+    import torch.distributed as dist
+    from ctransformers_b200 import LLM, Config, synth
+    from ctransformers_b200.tp import tensor_parallel_ticket
+    shape = getattr(synth, WL["shape"])
+    if world > 1:
+        ticket = tensor_parallel_ticket()
+    else:
+        ticket = None
+    llm = LLM(str(path), config=Config(context_length=CTX), tp=ticket)
+    ids = prompt_ids()
+    steps = max(1, min(args.steps, CTX - PROMPT - args.warmup - 1))
+    W = max(args.warmup, 3)
+    llm.eval(ids, batch_size=256)
+    tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    for _ in range(W):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    e2e_tokens = []
+    for _ in range(steps):
+        llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        e2e_tokens.append(tok)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # device-timed: K steps with the token fed back on the device (every rank picks from the same all-reduced logits)
+    llm._context = []
+    llm.eval(ids, batch_size=256)
+    first = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+    out = (C.c_int * (W + steps))()
+    assert llm.ctb_llm_decode_greedy(first, PROMPT, W, out) >= 0
+    barrier()
+    ms = llm.ctb_llm_decode_greedy(int(out[W - 1]), PROMPT + W, steps, out)
+    barrier()
+    clocks = sampler.summary()
+    assert ms > 0
+    ms = max_over_ranks(ms)
+    tokens_dev = list(out[:steps])
+    ranks_agree = all(t == tokens_dev for t in group.gather_ints(tokens_dev))
+    peak, peak_src = hbm_peak()
+    wbytes = int(llm.ctb_llm_weight_bytes_per_token())           # this rank's share
+    wb_max = max_over_ranks(float(wbytes))
+    achieved = wb_max / (ms / 1e3 / steps) / 1e9
+    launches = int(llm.ctb_llm_launches_per_token())
+    result = {
+        "metric": METRIC, "value": steps / (ms / 1e3), "unit": "tokens/s", "n_gpus": world, "steps": steps, "warmup": W, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": WL["name"] + " (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode", "global_batch": 1,
+                   "ctx": CTX, "prompt": PROMPT, "parallelism": f"tp{world} (column-parallel q/k/v/gate/up, row-parallel wo/down, {2 * shape.n_layer} all-reduces of {shape.n_embd} floats per token over NCCL)",
+                   "l2": "each rank streams its GBs of weights per step: inputs exceed the 126 MB L2"},
+        "clocks": clocks,
+        "e2e": {"value": steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 16 + 64 * 4, "d2h_bytes_per_step": 4 + 2064,
+                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step on every rank (same calls, same seed), wall clock, max over ranks"},
+        "gpu_launches": launches * steps, "launches_per_token": launches, "comm_nranks": world,
+        "roofline": {"bound": "hbm", "kernel": "k_step (all phases of a rank's step, exchanges included)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "weight_bytes_per_rank_per_step": wb_max,
+                     "how": "largest rank's weight bytes per step / device-timed step (so the NCCL exchanges and launch boundaries count against it)"},
+        "greedy_tokens_match_e2e": tokens_dev[:steps] == e2e_tokens[:steps], "ranks_agree": ranks_agree,
+    }
+    if rank == 0:
+        print(json.dumps(result))
+    del llm
+    group.close()
+
+
 def workload_config(n):
     return {"workload": WL["name"] + " (synthetic random quant blocks), batch=1 decode, ctx=512, 256-token prompt then decode",
             "global_batch": n, "ctx": CTX, "prompt": PROMPT, "parallelism": f"replicas x{n} (one sequence per GPU, no collective)",
@@ -263,8 +337,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="llama2-7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "tp"],
+                    help="tp: ONE sequence, layer weights tensor-sharded over the ranks (BASELINE configs[4]; implies --workload llama2-13b unless one is given)")
     args = ap.parse_args()
     global WL, METRIC, DTYPE
+    if args.mode == "tp" and args.workload == "llama2-7b" and "--workload" not in sys.argv:
+        args.workload = "llama2-13b"
     WL = WORKLOADS[args.workload]
     METRIC, DTYPE = WL["metric"], WL["dtype"]
 
@@ -290,6 +368,8 @@ def main():
 
     from ctransformers_b200 import AutoModelForCausalLM, synth
     path = ensure_model(rank, world, barrier)
+    if args.mode == "tp":
+        return run_tp(args, path, rank, world, local, barrier, max_over_ranks, group)
     if args.workload == "prefill2048":
         return run_prefill(args, path, rank, world, local, barrier, max_over_ranks, group)
     llm = AutoModelForCausalLM.from_pretrained(str(path), context_length=CTX)

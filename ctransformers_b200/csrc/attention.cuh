@@ -405,10 +405,11 @@ static __global__ void __launch_bounds__(ATTN_THREADS) k_attn(const AttnParams p
 }
 
 // ----------------------------------------------------------------------------------------- argmax
-// single block; writes the id of the largest logit (lowest id on ties) to *out
+// single block; writes the id of the largest logit (lowest id on ties) to out[0] and the number of logits equal to it to out[1]
 static __global__ void k_argmax(const float* logits, int n, int* out) {
   __shared__ float bv[32];
   __shared__ int bi[32];
+  __shared__ int ties;
   float best = -INFINITY;
   int idx = 0x7fffffff;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -426,8 +427,17 @@ static __global__ void k_argmax(const float* logits, int n, int* out) {
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); w++)
       if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
-    *out = idx;
+    out[0] = idx;
+    bv[0] = best;
+    ties = 0;
   }
+  __syncthreads();
+  const float top = bv[0];
+  int mine = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mine += logits[i] == top ? 1 : 0;
+  if (mine) atomicAdd(&ties, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) out[1] = ties;
 }
 
 }  // namespace ctb

@@ -14,6 +14,7 @@
 #include "sample_gpu.cuh"
 #include "stream.cuh"
 #include "tables.hpp"
+#include "tp_nccl.hpp"
 
 namespace ctb {
 
@@ -107,7 +108,7 @@ size_t engine_arena_bytes(const GGUFFile& g, const HParams& hp) {
   total += align_up((size_t)hp.n_ctx * (hp.head_dim() / 2) * 8, 256);
   const size_t qkv = (size_t)hp.n_embd + 2 * (size_t)hp.n_embd_gqa();
   total += 4 * (2 * (size_t)hp.n_embd + qkv + 4 * (size_t)hp.n_embd + 2 * (size_t)hp.n_ff + 2 * (size_t)hp.n_vocab) + 64 * 256 + 8192;
-  total += ((size_t)hp.n_layer * 8 + 8) * (sizeof(Phase) * 2 + 2 * 1024) + 8192;   // the step programs and their per-CTA tile ranges
+  total += ((size_t)hp.n_layer * 10 + 8) * (sizeof(Phase) * 2 + 2 * 1024) + 8192;   // the step programs and their per-CTA tile ranges
   total += 1 << 20;
   return total;
 }
@@ -161,19 +162,36 @@ struct Uploader {
   }
 };
 
-DevMat Engine::upload_matrix(const GGUFTensor& t, Uploader& up, int want_K, int want_M) {
+// rows [row0, row1) and elements [k0, k1) of every row (whole quantization blocks) are kept: a tensor-parallel shard
+// (column-parallel = a row range, row-parallel = a K range); the defaults keep the whole tensor.
+DevMat Engine::upload_matrix(const GGUFTensor& t, Uploader& up, int want_K, int want_M, int row0, int row1, int k0, int k1) {
   if (!supported_matrix_type(t.type)) throw std::runtime_error("tensor '" + t.name + "': quantization type " + std::to_string(t.type) + " is not supported by the B200 path");
   DevMat m;
   m.type = (int)t.type;
-  m.K = (int)t.ne[0];
-  m.M = (int)(t.ne[1] * t.ne[2] * t.ne[3]);
+  const int full_K = (int)t.ne[0], full_M = (int)(t.ne[1] * t.ne[2] * t.ne[3]);
   // the reference rejects a tensor whose shape does not follow from the hyper-parameters (llama.cpp:1345-1361 "wrong shape")
-  if (m.K != want_K || m.M != want_M)
+  if (full_K != want_K || full_M != want_M)
     throw std::runtime_error("tensor '" + t.name + "' has wrong shape; expected " + std::to_string(want_K) + " x " + std::to_string(want_M) + ", got " +
-                             std::to_string(m.K) + " x " + std::to_string(m.M));
-  m.nb = m.K / type_block_elems(t.type);
-  m.bytes = t.nbytes;
-  const size_t row_bytes = t.nbytes / (size_t)m.M;
+                             std::to_string(full_K) + " x " + std::to_string(full_M));
+  if (row1 < 0) row1 = full_M;
+  if (k1 < 0) k1 = full_K;
+  const int be = type_block_elems(t.type);
+  if (row0 < 0 || row1 > full_M || row0 >= row1 || k0 < 0 || k1 > full_K || k0 >= k1 || k0 % be || k1 % be)
+    throw std::runtime_error("tensor '" + t.name + "': shard does not fall on quantization block boundaries");
+  m.K = k1 - k0;
+  m.M = row1 - row0;
+  m.nb = m.K / be;
+  const size_t full_row_bytes = t.nbytes / (size_t)full_M;
+  const size_t row_bytes = (size_t)m.nb * type_block_bytes(t.type);
+  m.bytes = row_bytes * (size_t)m.M;
+  const uint8_t* src = t.data + (size_t)row0 * full_row_bytes;
+  std::vector<uint8_t> gathered;
+  if (m.K != full_K) {   // a K range: the kept blocks of every row, packed
+    gathered.resize(m.bytes);
+    const size_t off = (size_t)(k0 / be) * type_block_bytes(t.type);
+    for (int r = 0; r < m.M; r++) memcpy(gathered.data() + (size_t)r * row_bytes, src + (size_t)r * full_row_bytes + off, row_bytes);
+    src = gathered.data();
+  }
   int rows_per_chunk = (int)std::max<size_t>(ST_ROWS, UP_CHUNK / row_bytes / ST_ROWS * ST_ROWS);   // whole 16-row tiles
   if (row_bytes * ST_ROWS > UP_CHUNK) throw std::runtime_error("tensor '" + t.name + "': rows too long for the upload staging buffers");
   uint16_t *st = nullptr, *qs = nullptr, *d = nullptr;
@@ -182,7 +200,7 @@ DevMat Engine::upload_matrix(const GGUFTensor& t, Uploader& up, int want_K, int 
     st = (uint16_t*)alloc(st_matrix_bytes(m.type, m.M, m.nb));
     m.st = (const uint8_t*)st;
   } else {
-    const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, t.nbytes);
+    const PlaneSizes ps = plane_sizes(m.type, m.M, m.nb, m.bytes);
     qs = (uint16_t*)alloc(ps.qs);
     if (ps.d) d = (uint16_t*)alloc(ps.d);
     m.qs = (const uint8_t*)qs; m.d = d;
@@ -190,7 +208,7 @@ DevMat Engine::upload_matrix(const GGUFTensor& t, Uploader& up, int want_K, int 
   for (int r0 = 0; r0 < m.M; r0 += rows_per_chunk) {
     const int rows = std::min(rows_per_chunk, m.M - r0);
     const size_t n = (size_t)rows * row_bytes;
-    const int slot = up.push(t.data + (size_t)r0 * row_bytes, n);
+    const int slot = up.push(src + (size_t)r0 * row_bytes, n);
     if (kq) {
       const size_t sb = st_matrix_bytes(m.type, rows, m.nb);
       const int grid = (int)std::min<size_t>((sb / 2 + 255) / 256, (size_t)sm_count_ * 32);
@@ -251,7 +269,27 @@ static inline uint16_t host_f2h(float f) {
   return (uint16_t)(sign | hb);
 }
 
-Engine::Engine(const GGUFFile& g, const HParams& hp, int device) : hp_(hp), device_(device) {
+TPShard tp_shard(int n_embd, int n_head, int n_head_kv, int n_ff, int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world || n_head <= 0 || n_head_kv <= 0 || n_embd % n_head || n_head % n_head_kv) throw std::runtime_error("tensor parallel: bad shape or rank");
+  const int hd = n_embd / n_head;
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  const int group = 256 / gcd(256, hd);   // query heads per 256-element block of the attention output (2 for head_dim 128)
+  if ((hd * group) % 256 || n_head % group || n_ff % 256) throw std::runtime_error("tensor parallel: heads / n_ff do not tile into 256-element blocks");
+  auto split = [&](int units, int r0) {   // first element of part r0 when `units` are dealt as evenly as possible (the first units % world parts get one more)
+    const int base = units / world, extra = units % world;
+    return r0 * base + std::min(r0, extra);
+  };
+  TPShard s;
+  s.rank = rank; s.world = world;
+  s.head0 = split(n_head / group, rank) * group; s.head1 = split(n_head / group, rank + 1) * group;
+  s.ff0 = split(n_ff / 256, rank) * 256; s.ff1 = split(n_ff / 256, rank + 1) * 256;
+  const int per_kv = n_head / n_head_kv;
+  s.kv0 = s.head1 > s.head0 ? s.head0 / per_kv : 0;
+  s.kv1 = s.head1 > s.head0 ? (s.head1 - 1) / per_kv + 1 : 0;
+  return s;
+}
+
+Engine::Engine(const GGUFFile& g, const HParams& hp, int device, const TPShard& tp) : hp_(hp), tp_(tp), device_(device) {
   // everything acquired below is released by release() if the constructor throws (the destructor does not run then)
   try {
     init(g);
@@ -284,6 +322,20 @@ void Engine::init(const GGUFFile& g) {
   // ---- weights (shapes follow from the hyper-parameters: llama.cpp:1878-1934 llama, 1948-2012 falcon)
   const std::string pfx = "blk.";
   const int n_embd = hp_.n_embd, gqa = hp_.n_embd_gqa(), n_ff = hp_.n_ff;
+  nh_ = hp_.n_head; nkv_ = hp_.n_head_kv; nff_ = hp_.n_ff;
+  const int hd0 = hp_.head_dim();
+  if (tp_.world > 1) {
+    const int per_kv = hp_.n_head / hp_.n_head_kv;
+    if (hp_.falcon) throw std::runtime_error("tensor parallel mode covers the llama graph only");
+    if (!tp_.comm) throw std::runtime_error("tensor parallel mode needs a communicator");
+    if (tp_.head1 <= tp_.head0 || tp_.ff1 <= tp_.ff0) throw std::runtime_error("tensor parallel: more ranks than 256-element blocks to share out");
+    if (tp_.head0 % per_kv || tp_.head1 % per_kv) throw std::runtime_error("tensor parallel: a rank's query heads must cover whole KV groups");
+    nh_ = tp_.head1 - tp_.head0; nkv_ = tp_.kv1 - tp_.kv0; nff_ = tp_.ff1 - tp_.ff0;
+    prefill_on_ = false;   // prompts go through the single-token path (the batched kernel has no exchange step)
+  }
+  const int q0 = tp_.world > 1 ? tp_.head0 * hd0 : 0, q1 = tp_.world > 1 ? tp_.head1 * hd0 : n_embd;        // rows of wq = K range of wo
+  const int g0 = tp_.world > 1 ? tp_.kv0 * hd0 : 0, g1 = tp_.world > 1 ? tp_.kv1 * hd0 : gqa;               // rows of wk / wv
+  const int f0 = tp_.world > 1 ? tp_.ff0 : 0, f1 = tp_.world > 1 ? tp_.ff1 : n_ff;                          // rows of w1 / w3 = K range of w2
   {
     const GGUFTensor& te = g.need_tensor("token_embd.weight");
     if (!supported_matrix_type(te.type)) throw std::runtime_error("token_embd.weight: unsupported type");
@@ -313,13 +365,13 @@ void Engine::init(const GGUFFile& g) {
       wbytes += L.wqkv.bytes + L.wo.bytes + L.w3.bytes + L.w2.bytes;
     } else {
       L.ffn_norm = upload_vector(g, b + "ffn_norm.weight", true, n_embd);
-      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), up, n_embd, n_embd);
-      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), up, n_embd, gqa);
-      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), up, n_embd, gqa);
-      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), up, n_embd, n_embd);
-      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), up, n_embd, n_ff);
-      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), up, n_ff, n_embd);
-      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), up, n_embd, n_ff);
+      L.wq = upload_matrix(g.need_tensor(b + "attn_q.weight"), up, n_embd, n_embd, q0, q1);
+      L.wk = upload_matrix(g.need_tensor(b + "attn_k.weight"), up, n_embd, gqa, g0, g1);
+      L.wv = upload_matrix(g.need_tensor(b + "attn_v.weight"), up, n_embd, gqa, g0, g1);
+      L.wo = upload_matrix(g.need_tensor(b + "attn_output.weight"), up, n_embd, n_embd, 0, -1, q0, q1);
+      L.w1 = upload_matrix(g.need_tensor(b + "ffn_gate.weight"), up, n_embd, n_ff, f0, f1);
+      L.w2 = upload_matrix(g.need_tensor(b + "ffn_down.weight"), up, n_ff, n_embd, 0, -1, f0, f1);
+      L.w3 = upload_matrix(g.need_tensor(b + "ffn_up.weight"), up, n_embd, n_ff, f0, f1);
       wbytes += L.wq.bytes + L.wk.bytes + L.wv.bytes + L.wo.bytes + L.w1.bytes + L.w2.bytes + L.w3.bytes;
       if (act_format_for(L.w1.type) != act_format_for(L.w3.type)) throw std::runtime_error("ffn_gate / ffn_up use incompatible quantization families");
     }
@@ -359,19 +411,20 @@ void Engine::init(const GGUFFile& g) {
     CTB_CUDA(cudaMemcpy(rope_, tab.data(), tab.size() * sizeof(float2), cudaMemcpyHostToDevice));
   }
   // ---- KV cache + workspace
-  const size_t kv = (size_t)hp_.n_layer * hp_.n_ctx * hp_.n_embd_gqa();
-  const size_t vv = (size_t)hp_.n_layer * kv_ctx_pad(hp_.n_ctx) * hp_.n_embd_gqa();
+  const size_t gqa_l = (size_t)nkv_ * hp_.head_dim(), qw_l = (size_t)nh_ * hp_.head_dim();   // this rank's K/V and Q widths
+  const size_t kv = (size_t)hp_.n_layer * hp_.n_ctx * gqa_l;
+  const size_t vv = (size_t)hp_.n_layer * kv_ctx_pad(hp_.n_ctx) * gqa_l;
   kc_ = (uint16_t*)alloc(kv * 2);
   vc_ = (uint16_t*)alloc(vv * 2);
   CTB_CUDA(cudaMemset(kc_, 0, kv * 2));
   CTB_CUDA(cudaMemset(vc_, 0, vv * 2));
-  const size_t qkv = (size_t)hp_.n_embd + 2 * (size_t)hp_.n_embd_gqa();
+  const size_t qkv = qw_l + 2 * gqa_l;
   d_state_ = (int*)alloc(64);
   xa_ = (float*)alloc(hp_.n_embd * 4); xb_ = (float*)alloc(hp_.n_embd * 4);
   qkv_ = (float*)alloc(qkv * 4);
   attn_ = (float*)alloc(hp_.n_embd * 4); attn_o_ = (float*)alloc(hp_.n_embd * 4);
-  ffn_ = (float*)alloc((size_t)hp_.n_ff * 4);
-  ffn2_ = (float*)alloc((size_t)hp_.n_ff * 4);
+  ffn_ = (float*)alloc((size_t)nff_ * 4);
+  ffn2_ = (float*)alloc((size_t)nff_ * 4);
   d_logits_ = (float*)alloc((size_t)hp_.n_vocab * 4);
   d_embd_ = (float*)alloc(hp_.n_embd * 4);
   d_logits_keep_ = (float*)alloc((size_t)hp_.n_vocab * 4);
@@ -424,6 +477,8 @@ void Engine::release() {
   if (h_sample_) cudaFreeHost(h_sample_);
   h_sample_ = nullptr;
   if (ev_pick_) cudaEventDestroy(ev_pick_);
+  if (ev_sample_) cudaEventDestroy(ev_sample_);
+  ev_sample_ = nullptr;
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
   if (stream_ && own_stream_) cudaStreamDestroy(stream_);
@@ -461,8 +516,22 @@ void Engine::push_matvec(MVParams& p, int kind) {
   ops_.push_back(op);
 }
 
+void Engine::tp_all_reduce(float* buf, int n) {
+  const NcclApi& nccl = NcclApi::get();
+  nccl.check(nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)tp_.comm, stream_), "all-reduce");
+}
+
 void Engine::build_ops() {
-  const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = hp_.n_head_kv, gqa = hp_.n_embd_gqa();
+  // nh_ / nkv_ / nff_ are this rank's share (the whole model without tensor parallelism)
+  const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = nkv_, gqa = nkv_ * hp_.head_dim(), qw = nh_ * hp_.head_dim();
+  const bool tp = tp_.world > 1;
+  const bool tp_lead = tp_.rank == 0;   // the rank whose partial sum carries the residual
+  auto push_xchg = [&](float* buf) {    // all-reduce of a row-parallel mat-vec's partial sums (+ the residual, once)
+    StepOp op{};
+    op.ph.kind = PH_XCHG;
+    op.ph.em.out = buf; op.ph.em.K = n_embd;
+    ops_.push_back(op);
+  };
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
   ops_.clear();
   {
@@ -480,7 +549,7 @@ void Engine::build_ops() {
     uint16_t* vc = vc_ + (size_t)il * gqa * kv_ctx_pad(hp_.n_ctx);
     AttnParams ap{};
     ap.kc = kc; ap.vc = vc; ap.out = attn_; ap.exp_tab = exp_tab_; ap.state = d_state_; ap.kq_scale = kq_scale;
-    ap.n_head = hp_.n_head; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx; ap.rope = rope_; ap.neox = hp_.falcon ? 1 : 0;
+    ap.n_head = nh_; ap.n_kv = n_kv; ap.hd = hd; ap.n_ctx = hp_.n_ctx; ap.rope = rope_; ap.neox = hp_.falcon ? 1 : 0;
     auto push_attn = [&]() {
       StepOp op{};
       op.ph.kind = PH_ATTN;
@@ -489,14 +558,14 @@ void Engine::build_ops() {
     };
 
     if (!hp_.falcon) {
-      float* q = qkv_; float* k = qkv_ + n_embd; float* v = qkv_ + n_embd + gqa;
+      float* q = qkv_; float* k = qkv_ + qw; float* v = qkv_ + qw + gqa;
       {  // attention_norm + wq/wk/wv
         MVParams p{};
         p.x = x; p.norm_w = L.attn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
         const DevMat* ws[3] = {&L.wq, &L.wk, &L.wv};
         float* outs[3] = {q, k, v};
         bool done[3] = {false, false, false};
-        ap.q = q; ap.k = k; ap.v = v; ap.q_stride = n_embd; ap.kv_stride = gqa;
+        ap.q = q; ap.k = k; ap.v = v; ap.q_stride = qw; ap.kv_stride = gqa;
         for (int i = 0; i < 3; i++) {   // group tensors that share an activation format into one launch
           if (done[i]) continue;
           p.act = act_format_for(ws[i]->type); p.nseg = 0;
@@ -508,9 +577,10 @@ void Engine::build_ops() {
       push_attn();
       {  // wo + residual
         MVParams p{};
-        p.x = attn_; p.norm_mode = NORM_NONE; p.K = n_embd; p.act = act_format_for(L.wo.type); p.nseg = 1;
-        p.seg[0] = seg(L.wo, y, EPI_ADD, x);
+        p.x = attn_; p.norm_mode = NORM_NONE; p.K = qw; p.act = act_format_for(L.wo.type); p.nseg = 1;
+        p.seg[0] = (!tp || tp_lead) ? seg(L.wo, y, EPI_ADD, x) : seg(L.wo, y);
         push_matvec(p, MVK_WO);
+        if (tp) push_xchg(y);
       }
       {  // ffn_norm + gate and up projections as two independent row sets: silu(gate) is stored, the product with up is formed
          // where ffn_down stages its input
@@ -522,9 +592,10 @@ void Engine::build_ops() {
       }
       {  // w2 on silu(gate)*up, + residual
         MVParams p{};
-        p.x = ffn_; p.x2 = ffn2_; p.x_mode = 1; p.norm_mode = NORM_NONE; p.K = hp_.n_ff; p.act = act_format_for(L.w2.type); p.nseg = 1;
-        p.seg[0] = seg(L.w2, x, EPI_ADD, y);
+        p.x = ffn_; p.x2 = ffn2_; p.x_mode = 1; p.norm_mode = NORM_NONE; p.K = nff_; p.act = act_format_for(L.w2.type); p.nseg = 1;
+        p.seg[0] = (!tp || tp_lead) ? seg(L.w2, x, EPI_ADD, y) : seg(L.w2, x);
         push_matvec(p, MVK_DOWN);
+        if (tp) push_xchg(x);
       }
       // x now holds the next layer's input
     } else {
@@ -583,7 +654,7 @@ void Engine::build_ops() {
   bool any_stream = false;
   for (const StepOp& op : ops_) any_stream |= op.ph.kind == PH_MATVEC && op.stream;
   std::vector<Phase> phs;
-  for (const StepOp& op : ops_) if (op.ph.kind != PH_MATVEC || op.stream) phs.push_back(op.ph);
+  for (const StepOp& op : ops_) if (op.ph.kind != PH_XCHG && (op.ph.kind != PH_MATVEC || op.stream)) phs.push_back(op.ph);
   const StepLaunch sl = step_launch_shape(phs.data(), (int)phs.size(), sm_count_, step_max_dyn_smem());
   step_grid_ = sl.grid; step_slots_ = sl.n_slots; step_smem_ = sl.smem;
   if (const char* e = getenv("CTB_ST_SLOTS")) {   // A/B knob: fewer ring slots = less prefetch in flight
@@ -606,7 +677,7 @@ void Engine::upload_prog(Phase* dst, int* dst_bounds, const std::vector<StepOp>&
   for (size_t i = 0; i < ops.size(); i++) phs[i] = ops[i].ph;
   CTB_CUDA(cudaMemcpy(dst, phs.data(), phs.size() * sizeof(Phase), cudaMemcpyHostToDevice));
   std::vector<Phase> run = phs;
-  for (size_t i = 0; i < ops.size(); i++) if (ops[i].ph.kind == PH_MATVEC && !ops[i].stream) run[i].kind = -1;   // not a step-kernel phase
+  for (size_t i = 0; i < ops.size(); i++) if (ops[i].ph.kind == PH_XCHG || (ops[i].ph.kind == PH_MATVEC && !ops[i].stream)) run[i].kind = -1;   // not a step-kernel phase
   const std::vector<int> b = step_bounds(run.data(), (int)run.size(), sm_count_);
   CTB_CUDA(cudaMemcpy(dst_bounds, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
 }
@@ -618,7 +689,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, co
   launches_per_step_ = 0;
   StepLaunch step_shape_;
   step_shape_.grid = step_grid_; step_shape_.n_slots = step_slots_; step_shape_.smem = step_smem_;
-  auto capable = [&](const StepOp& op) { return op.ph.kind != PH_MATVEC || op.stream; };
+  auto capable = [&](const StepOp& op) { return op.ph.kind != PH_XCHG && (op.ph.kind != PH_MATVEC || op.stream); };
   int i = 0;
   while (i < n) {
     const StepOp& op = ops[i];
@@ -641,7 +712,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, co
         break;
       case PH_ATTN: {
         cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(hp_.n_head, 1, hp_.head_dim() / ATTN_CH); cfg.blockDim = dim3(ATTN_THREADS);
+        cfg.gridDim = dim3(nh_, 1, hp_.head_dim() / ATTN_CH); cfg.blockDim = dim3(ATTN_THREADS);
         cfg.dynamicSmemBytes = attn_smem_bytes(hp_.n_ctx, hp_.head_dim()); cfg.stream = stream_;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -651,6 +722,10 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, co
         launches_per_step_++;
         mark(1);
       } break;
+      case PH_XCHG:
+        tp_all_reduce(op.ph.em.out, op.ph.em.K);
+        mark(3);
+        break;
       case PH_PICK:
         k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
         k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
@@ -684,7 +759,7 @@ void Engine::mark(int kind) {
 // One eager decode step, one kernel per op (un-fused), a CUDA event around every kernel: the kernel classes' share of a step.
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
   DeviceGuard dev_guard(device_);
-  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
   CTB_CUDA(cudaMemcpyAsync(d_state_, h_state_, 16, cudaMemcpyHostToDevice, stream_));
@@ -712,7 +787,7 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
 // keep the mat-vecs of kind k (0 = all).  with_attn: keep the attention phases too (times the dependency chain as it is).
 double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   if (!mask) mask = ~0u;
-  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   DeviceGuard dev_guard(device_);
   std::vector<StepOp> sel;
   for (int i = 0; i <= n_body_; i++)
@@ -752,7 +827,7 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
 // first weight item ready, phase done + 4 stamps of the grid barrier in front of the phase).  out: n_phases x {kind, mvk} then n_phases x n_cta x 8 stamps; returns n_phases or -(words needed).
 long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
   DeviceGuard dev_guard(device_);
-  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   const int n = n_body_ + 1;
   for (int i = 0; i < n; i++)
     if (ops_[i].ph.kind == PH_MATVEC && !ops_[i].stream) return 0;
@@ -827,19 +902,45 @@ void Engine::build_graphs() {
 // simply runs after it (stream order) and overwrites the same KV slot, so a wrong guess costs time, never correctness.
 void Engine::after_eval(int next_pos) {
   spec_pending_ = false;
+  spec_deferred_ = false;
   spec_pos_ = -1;
   // the look-ahead step writes K/V slot next_pos: only when nothing valid can live there (append-only decoding).  A caller
   // that re-evaluates an earlier position and later continues past it keeps its cache contents.
   if (!spec_on_ || next_pos >= hp_.n_ctx || next_pos < kv_high_) return;
   k_argmax<<<1, 1024, 0, stream_>>>(d_logits_, hp_.n_vocab, d_state_ + 4);
   k_advance<<<1, 1, 0, stream_>>>(d_state_, d_tokens_out_);
-  CTB_CUDA(cudaMemcpyAsync(h_spec_tok_, d_state_, 4, cudaMemcpyDeviceToHost, stream_));
+  CTB_CUDA(cudaMemcpyAsync(h_spec_tok_, d_state_ + 4, 8, cudaMemcpyDeviceToHost, stream_));   // {greedy pick, how many logits equal the maximum}
   CTB_CUDA(cudaEventRecord(ev_pick_, stream_));
   spec_pos_ = next_pos;
   if (spec_streak_ >= 2) {
-    CTB_CUDA(cudaGraphLaunch(graph_full_, stream_));
-    spec_pending_ = true;
+    // The persistent step kernel fills every SM, so whatever is enqueued behind the look-ahead step waits for all of it.  A
+    // caller whose sample() runs the device sampler (sample_gpu.cuh) therefore gets the look-ahead launched from there, right
+    // behind the sampler kernel; a caller who takes the greedy pick needs no kernel and gets it launched here, before the wait.
+    if (sampler_mode_) spec_deferred_ = true;
+    else {
+      CTB_CUDA(cudaGraphLaunch(graph_full_, stream_));
+      spec_pending_ = true;
+    }
   }
+}
+
+void Engine::launch_deferred_spec() {
+  if (!spec_deferred_) return;
+  spec_deferred_ = false;
+  CTB_CUDA(cudaGraphLaunch(graph_full_, stream_));
+  spec_pending_ = true;
+}
+
+// The greedy pick of the last eval (what top_k = 1 without a repetition penalty selects, llama.cpp:3832-3857 + 4215-4240: one
+// candidate survives, the draw is certain) if the engine computed it: id, or -1 when it did not (look-ahead off, context full,
+// non-appending eval) or when several logits share the maximum (std::partial_sort's choice among equals is the reference's).
+int Engine::greedy_pick() {
+  if (spec_pos_ < 0) return -1;
+  DeviceGuard dev_guard(device_);
+  CTB_CUDA(cudaEventSynchronize(ev_pick_));
+  sampler_mode_ = false;
+  launch_deferred_spec();
+  return h_spec_tok_[1] == 1 ? h_spec_tok_[0] : -1;
 }
 
 void Engine::eval(const int* tokens, int n, int n_past) {
@@ -885,13 +986,17 @@ int Engine::topk_candidates(const int* last, int n_last, float penalty, int k, i
     d_last_ = (int*)alloc(SG_MAX_LAST * 4 + 16);
     CTB_CUDA(cudaMallocHost(&h_sample_, sizeof(SampleGpuOut) + SG_MAX_LAST * 4));
   }
+  if (!ev_sample_) CTB_CUDA(cudaEventCreateWithFlags(&ev_sample_, cudaEventDisableTiming));
+  sampler_mode_ = true;
   int* h_last = (int*)(h_sample_ + 1);
   for (int i = 0; i < n_last; i++) h_last[i] = last[i];
   if (n_last > 0) CTB_CUDA(cudaMemcpyAsync(d_last_, h_last, (size_t)n_last * 4, cudaMemcpyHostToDevice, stream_));
   k_sample_topk<<<1, SG_THREADS, 0, stream_>>>(d_logits_keep_, hp_.n_vocab, d_last_, n_last, penalty, std::min(k, hp_.n_vocab), d_sample_);
   CTB_CUDA(cudaGetLastError());
   CTB_CUDA(cudaMemcpyAsync(h_sample_, d_sample_, sizeof(SampleGpuOut), cudaMemcpyDeviceToHost, stream_));
-  CTB_CUDA(cudaStreamSynchronize(stream_));
+  CTB_CUDA(cudaEventRecord(ev_sample_, stream_));
+  launch_deferred_spec();                          // the look-ahead step runs while the host finishes the draw
+  CTB_CUDA(cudaEventSynchronize(ev_sample_));
   const int n = h_sample_->count;
   if (n < 0 || n > SG_MAX_OUT) return -1;
   for (int i = 0; i < n; i++) { ids[i] = h_sample_->id[i]; logits[i] = h_sample_->logit[i]; }
@@ -922,11 +1027,12 @@ void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, in
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   bool hit = false;
   if (spec_pos_ >= 0) {
-    const bool was_pending = spec_pending_;
+    const bool was_pending = spec_pending_;   // (a deferred look-ahead nobody launched is simply dropped)
+    spec_deferred_ = false;
     bool guessed = false;
     if (n == 1 && pos[0] == spec_pos_ && n_total[0] == pos[0] + 1) {
       CTB_CUDA(cudaEventSynchronize(ev_pick_));
-      guessed = *h_spec_tok_ == tokens[0];
+      guessed = h_spec_tok_[0] == tokens[0];
     }
     spec_streak_ = guessed ? spec_streak_ + 1 : 0;
     hit = guessed && was_pending;
@@ -959,7 +1065,7 @@ void Engine::eval_list(const int* tokens, const int* pos, const int* n_total, in
 }
 
 bool Engine::ensure_prefill() {
-  if (!prefill_on_) return false;
+  if (!prefill_on_ || tp_.world > 1) return false;
   if (pf_ && pf_->tried) return pf_->ok;
   if (!pf_) pf_ = new PrefillState();
   PrefillState& P = *pf_;
@@ -1068,7 +1174,7 @@ void Engine::prefill_batch(const int* tokens, const int* pos, const int* n_total
 
 double Engine::decode_greedy(int first_token, int n_past, int n_steps, int* out_tokens) {
   if (n_steps <= 0) return 0.0;
-  spec_pending_ = false; spec_pos_ = -1; spec_streak_ = 0;
+  spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (n_steps > tokens_out_cap_) throw std::runtime_error("decode_greedy: too many steps");
   if (n_past + n_steps > hp_.n_ctx) throw std::runtime_error("decode_greedy: would run past the context length");
   kv_high_ = std::max(kv_high_, n_past + n_steps);

@@ -18,6 +18,18 @@
 
 namespace ctb {
 
+// Tensor-sharded mode (BASELINE configs[4]): one process per GPU; rank r of `world` owns the query heads
+// [head0, head1) (with their KV heads), the n_ff range [ff0, ff1) — always whole 256-element blocks — and a replica of the
+// embedding table, the norms and the output head.  Column-parallel wq / wk / wv / w1 / w3, row-parallel wo / w2, two
+// all-reduces of n_embd floats per layer (NCCL over NVLink, captured in the step's CUDA graph).
+struct TPShard {
+  int rank = 0, world = 1;
+  int head0 = 0, head1 = 0, kv0 = 0, kv1 = 0, ff0 = 0, ff1 = 0;
+  void* comm = nullptr;   // ncclComm_t
+};
+// the shard of rank r (same arithmetic as ctransformers_b200/tp_plan.py; throws when the shape does not tile into 256-blocks)
+TPShard tp_shard(int n_embd, int n_head, int n_head_kv, int n_ff, int rank, int world);
+
 struct HParams {
   bool falcon = false;
   int n_vocab = 0, n_ctx_train = 0, n_embd = 0, n_ff = 0, n_head = 0, n_head_kv = 0, n_layer = 0, n_rot = 0;
@@ -44,7 +56,7 @@ struct EvalStats { double last_eval_ms = 0; long launches = 0; size_t weight_byt
 
 class Engine {
  public:
-  Engine(const GGUFFile& g, const HParams& hp, int device);
+  Engine(const GGUFFile& g, const HParams& hp, int device, const TPShard& tp = TPShard());
   ~Engine();
   Engine(const Engine&) = delete;
   Engine& operator=(const Engine&) = delete;
@@ -73,6 +85,8 @@ class Engine {
   // Device half of the sampler (sample_gpu.cuh): candidates >= the k-th largest penalised logit.  Returns their count, or -1
   // when the device path does not apply (window too long, k too large).
   int topk_candidates(const int* last, int n_last, float penalty, int k, int* ids, float* logits);
+  // The last eval's greedy pick when the engine has it and it is unambiguous (a unique maximum), else -1.
+  int greedy_pick();
   const HParams& hparams() const { return hp_; }
   EvalStats stats;
   void set_stream(cudaStream_t s);   // run on a caller-owned stream (bench: torch's current stream)
@@ -80,6 +94,9 @@ class Engine {
 
  private:
   HParams hp_;
+  TPShard tp_;
+  int nh_ = 0, nkv_ = 0, nff_ = 0;   // this rank's query heads, KV heads and n_ff slice (the whole model when world == 1)
+  void tp_all_reduce(float* buf, int n);
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   bool own_stream_ = true;
@@ -113,6 +130,10 @@ class Engine {
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev_pick_ = nullptr;
   // speculative next step (see after_eval)
   bool spec_on_ = true, spec_pending_ = false;
+  bool spec_deferred_ = false;   // a look-ahead step is due but waits for the device sampler to be enqueued first
+  bool sampler_mode_ = false;    // the caller's last sample() ran the device sampler kernel (not the greedy pick)
+  cudaEvent_t ev_sample_ = nullptr;
+  void launch_deferred_spec();
   int spec_pos_ = -1, spec_streak_ = 0;
   int kv_high_ = 0;              // one past the highest position any eval has written
   int* h_spec_tok_ = nullptr;
@@ -123,7 +144,8 @@ class Engine {
 
   void init(const GGUFFile& g);
   void release();
-  DevMat upload_matrix(const GGUFTensor& t, struct Uploader& up, int want_K, int want_M);
+  // rows [row0, row1) and K range [k0, k1) of the tensor (defaults: all of it); the shape check is against the FULL tensor
+  DevMat upload_matrix(const GGUFTensor& t, struct Uploader& up, int want_K, int want_M, int row0 = 0, int row1 = -1, int k0 = 0, int k1 = -1);
   const float* upload_vector(const GGUFFile& g, const std::string& name, bool required, int want_n);
   // the per-token schedule
   std::vector<StepOp> ops_;      // EMBED, layers..., HEAD, PICK

@@ -22,11 +22,17 @@
 #include "engine.cuh"
 #include "gguf.hpp"
 #include "sampler.hpp"
+#include "tp_nccl.hpp"
 #include "vocab.hpp"
 
 using namespace ctb;
 
 struct LLM {
+  ~LLM() {
+    engine.reset();   // before the communicator its graphs captured
+    if (comm) NcclApi::get().CommDestroy((ncclComm_t)comm);
+  }
+  void* comm = nullptr;   // ncclComm_t of the tensor-sharded mode
   std::unique_ptr<GGUFFile> file;
   Vocab vocab;
   HParams hp;
@@ -76,7 +82,7 @@ static HParams read_hparams(const GGUFFile& g, const std::string& arch, int n_ct
 
 extern "C" {
 
-LLM* ctransformers_llm_create(const char* model_path, const char* model_type, const ctransformers_config config) {
+static LLM* create_llm(const char* model_path, const char* model_type, const ctransformers_config config, int rank, int world, const void* unique_id) {
   try {
     std::string type = model_type ? model_type : "";
     type.erase(std::remove_if(type.begin(), type.end(), [](const char c) { return !std::isalnum((unsigned char)c); }), type.end());
@@ -98,7 +104,20 @@ LLM* ctransformers_llm_create(const char* model_path, const char* model_type, co
     int device = 0;
     if (const char* env = getenv("CT_DEVICE")) device = atoi(env);
     else if (const char* lr = getenv("LOCAL_RANK")) device = atoi(lr) % ndev;
-    llm->engine.reset(new Engine(*llm->file, llm->hp, device));
+    TPShard tp;
+    if (world > 1) {
+      if (!unique_id) throw std::runtime_error("tensor parallel: no communicator id");
+      tp = tp_shard(llm->hp.n_embd, llm->hp.n_head, llm->hp.n_head_kv, llm->hp.n_ff, rank, world);
+      if (cudaSetDevice(device) != cudaSuccess) throw std::runtime_error("cudaSetDevice failed");
+      const NcclApi& nccl = NcclApi::get();
+      ncclUniqueId id;
+      memcpy(&id, unique_id, sizeof(id));
+      ncclComm_t comm = nullptr;
+      nccl.check(nccl.CommInitRank(&comm, world, id, rank), "communicator init");
+      llm->comm = comm;
+      tp.comm = comm;
+    }
+    llm->engine.reset(new Engine(*llm->file, llm->hp, device, tp));
     return llm.release();
   } catch (const std::exception& e) {
     fprintf(stderr, "ctransformers-b200: failed to load model: %s\n", e.what());
@@ -107,6 +126,40 @@ LLM* ctransformers_llm_create(const char* model_path, const char* model_type, co
     fprintf(stderr, "ctransformers-b200: failed to load model\n");
     return nullptr;
   }
+}
+
+LLM* ctransformers_llm_create(const char* model_path, const char* model_type, const ctransformers_config config) {
+  return create_llm(model_path, model_type, config, 0, 1, nullptr);
+}
+
+int ctb_tp_unique_id(void* out, int cap) {
+  try {
+    if (!out || cap < (int)sizeof(ncclUniqueId)) return -(int)sizeof(ncclUniqueId);
+    const NcclApi& nccl = NcclApi::get();
+    ncclUniqueId id;
+    nccl.check(nccl.GetUniqueId(&id), "unique id");
+    memcpy(out, &id, sizeof(id));
+    return (int)sizeof(id);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "ctransformers-b200: %s\n", e.what());
+    return 0;
+  } catch (...) { return 0; }
+}
+
+LLM* ctb_llm_create_tp(const char* model_path, const char* model_type, const ctransformers_config config, int rank, int world, const void* unique_id) {
+  if (world < 1 || rank < 0 || rank >= world) {
+    fprintf(stderr, "ctransformers-b200: bad tensor-parallel rank %d of %d\n", rank, world);
+    return nullptr;
+  }
+  return create_llm(model_path, model_type, config, rank, world, unique_id);
+}
+
+int ctb_tp_shard(int n_embd, int n_head, int n_head_kv, int n_ff, int rank, int world, int* out6) {
+  try {
+    const TPShard s = tp_shard(n_embd, n_head, n_head_kv, n_ff, rank, world);
+    out6[0] = s.head0; out6[1] = s.head1; out6[2] = s.kv0; out6[3] = s.kv1; out6[4] = s.ff0; out6[5] = s.ff1;
+    return 0;
+  } catch (...) { return -1; }
 }
 
 void ctransformers_llm_delete(LLM* llm) { delete llm; }
@@ -174,6 +227,15 @@ int ctransformers_llm_sample(LLM* llm, const int* last_tokens, const int n_last,
     llm->rng.seed((unsigned)seed);
     if (llm->engine->lazy_logits()) {
       // nobody holds a host view of the logits: penalty + top-k run on the device, only the candidates come back
+      if (top_k == 1 && (repetition_penalty == 1.0f || n_last <= 0)) {
+        // greedy: one candidate survives top-k, so top-p / temperature / the draw cannot change it (llama.cpp:3832-3857,
+        // 4215-4240).  The engine already holds the arg-max of these logits (its look-ahead pick); equal maxima fall through.
+        const int pick = llm->engine->greedy_pick();
+        if (pick >= 0) {
+          llm->gpu_samples++;
+          return pick;
+        }
+      }
       int ids[256];
       float lg[256];
       const int count = llm->engine->topk_candidates(last_tokens, n_last, repetition_penalty, top_k, ids, lg);

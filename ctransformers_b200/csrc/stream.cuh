@@ -508,7 +508,8 @@ struct TileSpace {
 
 // ---------------------------------------------------------------------------------------------
 // Phases of a step
-enum : int { PH_MATVEC = 0, PH_ATTN = 1, PH_EMBED = 2, PH_PICK = 3 };
+enum : int { PH_MATVEC = 0, PH_ATTN = 1, PH_EMBED = 2, PH_PICK = 3,
+              PH_XCHG = 4 };   // PH_XCHG: host-side schedule entry only (tensor-parallel all-reduce between two launches), never a kernel phase
 struct EmbedParams { const uint8_t* table; size_t row_bytes; const int* tokens; float* out; int type, K, n_vocab; };
 struct PickParams { const float* logits; int* state; int* out_tokens; int n; };
 struct alignas(16) Phase {

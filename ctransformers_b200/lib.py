@@ -66,6 +66,9 @@ EXTRA_PROTOTYPES = {
     "ctb_llm_load_ms": (C.c_double, [_P]),
     "ctb_llm_device_samples": (C.c_long, [_P]),
     "ctb_llm_set_stream": (None, [_P, C.c_void_p]),
+    "ctb_tp_unique_id": (C.c_int, [_P, C.c_int]),
+    "ctb_llm_create_tp": (_P, [C.c_char_p, C.c_char_p, ConfigStruct, C.c_int, C.c_int, _P]),
+    "ctb_tp_shard": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _IP]),
     "ctb_llm_decode_greedy": (C.c_double, [_P, C.c_int, C.c_int, C.c_int, _IP]),
     "ctb_llm_profile_step": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double), _IP]),
     "ctb_llm_time_matvec_only": (C.c_double, [_P, C.c_int, C.POINTER(C.c_long)]),

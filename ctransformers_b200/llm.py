@@ -95,8 +95,10 @@ def _split_incomplete_utf8(seq: bytes):
 
 
 class LLM:
-    def __init__(self, model_path: str, model_type: Optional[str] = None, *, config: Optional[Config] = None, lib: Optional[str] = None):
-        """Loads a GGUF model onto the GPU (reference: ctransformers/llm.py:212-259)."""
+    def __init__(self, model_path: str, model_type: Optional[str] = None, *, config: Optional[Config] = None, lib: Optional[str] = None, tp=None):
+        """Loads a GGUF model onto the GPU (reference: ctransformers/llm.py:212-259).
+        tp = (rank, world, unique_id_bytes) loads this process's shard of the tensor-sharded mode (ctransformers_b200/tp.py;
+        an extension: the reference has no multi-GPU path)."""
         self._config = config or Config()
         self._model_path, self._llm, self._lib, self._context = model_path, None, None, []
         if not Path(model_path).is_file():
@@ -107,7 +109,11 @@ class LLM:
                                  "  AutoModelForCausalLM.from_pretrained(..., model_type='...')\n\n")
             model_type = "gguf"
         self._lib = load_library(lib)
-        self._llm = self._lib.ctransformers_llm_create(model_path.encode(), model_type.encode(), self._config.to_struct())
+        if tp is not None and tp[1] > 1:
+            rank, world, uid = tp
+            self._llm = self._lib.ctb_llm_create_tp(model_path.encode(), model_type.encode(), self._config.to_struct(), rank, world, bytes(uid))
+        else:
+            self._llm = self._lib.ctransformers_llm_create(model_path.encode(), model_type.encode(), self._config.to_struct())
         if self._llm is None:
             raise RuntimeError(f"Failed to create LLM '{model_type}' from '{model_path}'.")
         self._model_type = self.ctransformers_llm_architecture().decode() or model_type

@@ -70,6 +70,16 @@ unsigned long long ctb_llm_weight_bytes_per_token(LLM* llm); /* algorithmic weig
 long ctb_llm_device_samples(LLM* llm);
 /* wall-clock milliseconds the weight upload took (mmap -> pinned staging -> H2D -> repack, pipelined; engine.cu Uploader) */
 double ctb_llm_load_ms(LLM* llm);
+/* Tensor-sharded mode (BASELINE configs[4]; the reference's closest facility is layer offload to ONE GPU, llm.h:20 gpu_layers —
+ * it has no multi-GPU path).  One process per GPU: rank 0 calls ctb_tp_unique_id (128 bytes, a ncclUniqueId) and hands the
+ * bytes to the other ranks by any host channel; every rank then calls ctb_llm_create_tp.  Each rank keeps its query heads
+ * (with their KV heads) and its n_ff slice, cut on 256-element block boundaries (ctb_tp_shard reports the ranges:
+ * head0, head1, kv0, kv1, ff0, ff1), and the step exchanges two n_embd-float all-reduces per layer over NCCL.  llama graph
+ * only; every rank must make the same calls in the same order and ends up with the same logits. */
+int ctb_tp_unique_id(void* out, int cap);                     /* bytes written (128), or -needed */
+LLM* ctb_llm_create_tp(const char* model_path, const char* model_type, const ctransformers_config config, int rank, int world,
+                       const void* unique_id);
+int ctb_tp_shard(int n_embd, int n_head, int n_head_kv, int n_ff, int rank, int world, int* out6);
 void ctb_llm_set_stream(LLM* llm, void* cuda_stream);        /* run on a caller-owned cudaStream_t */
 /* n_steps greedy decode steps with the token fed back on the device (no host round trip per token);
  * returns the device-timed milliseconds, < 0 on error.  Logits of the last step land in logits_data. */

@@ -60,6 +60,11 @@ typedef struct {
     /* optional trace: if non-NULL, receives the residual stream after every layer of the LAST evaluated token,
      * [n_layer][n_embd], plus (trace_attn) the attention block's merged output [n_layer][n_embd] */
     float *trace_layer_out, *trace_attn;
+    /* tensor-parallel summation mode (NOT a reference behaviour: the restatement of what ctransformers_b200's sharded engine
+     * computes, csrc/engine.cu build_ops): wo / w2 are row-parallel, rank r multiplies the K range [split[r], split[r+1]) of the
+     * activation as a matrix of its own (its fp32 chains start at zero at its first block), rank 0 adds the residual, and the
+     * ranks' vectors are added in rank order (world 2: a single commutative fp32 add, i.e. exactly what an all-reduce gives). */
+    int tp_world; int tp_wo[17], tp_w2[17];
 } orc_model;
 
 orc_model *orc_model_new(int falcon, int n_vocab, int n_embd, int n_ff, int n_head, int n_head_kv, int n_layer, int n_ctx, float eps,
@@ -89,6 +94,12 @@ void orc_model_set_vec(orc_model *m, int layer, int slot, const float *data) {
     orc_layer *L = &m->layers[layer];
     const float **dst[5] = {&L->attn_norm, &L->attn_norm_b, &L->attn_norm2, &L->attn_norm2_b, &L->ffn_norm};
     *dst[slot] = data;
+}
+int orc_model_set_tp(orc_model *m, int world, const int *wo_split, const int *w2_split) {
+    if (world < 1 || world > 16) return -1;
+    m->tp_world = world;
+    for (int r = 0; r <= world; r++) { m->tp_wo[r] = wo_split[r]; m->tp_w2[r] = w2_split[r]; }
+    return 0;
 }
 void orc_model_set_trace(orc_model *m, float *layer_out, float *attn) { m->trace_layer_out = layer_out; m->trace_attn = attn; }
 
@@ -125,6 +136,22 @@ static void matvec(const orc_mat *w, const float *x, float *y) {
     } else {
         orc_mul_mat(w->type, w->data, x, y, w->K, w->M, 1);
     }
+}
+
+/* x = all-reduce over ranks of (rank 0: x + W_0 a_0; rank r: W_r a_r), W_r = columns [split[r], split[r+1]) of w (quantized types only) */
+static void matvec_row_parallel(const orc_mat *w, const float *a, float *x, int world, const int *split) {
+    const int be = (w->type == 2 || w->type == 8) ? 32 : 256, bb = orc_sizeof_block(w->type);
+    const size_t full_row = (size_t)(w->K / be) * bb;
+    float *part = (float *)malloc(sizeof(float) * w->M);
+    for (int r = 0; r < world; r++) {
+        const int k0 = split[r], k1 = split[r + 1], nbl = (k1 - k0) / be;
+        char *sl = (char *)malloc((size_t)w->M * nbl * bb);
+        for (int m = 0; m < w->M; m++) memcpy(sl + (size_t)m * nbl * bb, (const char *)w->data + (size_t)m * full_row + (size_t)(k0 / be) * bb, (size_t)nbl * bb);
+        orc_mul_mat(w->type, sl, a + k0, part, k1 - k0, w->M, 1);
+        for (int i = 0; i < w->M; i++) x[i] = x[i] + part[i];
+        free(sl);
+    }
+    free(part);
 }
 
 /* One token at absolute position pos.  x: [n_embd] residual stream in/out. */
@@ -164,14 +191,20 @@ static void eval_token(orc_model *m, int token, int pos, int n_total, int want_o
         }
         if (want_out && m->trace_attn) memcpy(m->trace_attn + (size_t)il * E, att, sizeof(float) * E);
         if (!m->falcon) {
-            matvec(&L->wo, att, tmp);
-            for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];              /* inpFF = cur + inpSA */
+            if (m->tp_world > 1) matvec_row_parallel(&L->wo, att, x, m->tp_world, m->tp_wo);
+            else {
+                matvec(&L->wo, att, tmp);
+                for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];          /* inpFF = cur + inpSA */
+            }
             orc_rms_norm_mul(x, L->ffn_norm, nrm, E, m->eps);
             matvec(&L->w3, nrm, u); matvec(&L->w1, nrm, g);
             orc_silu(g, g, FF);
             for (int i = 0; i < FF; i++) g[i] = g[i] * u[i];
-            matvec(&L->w2, g, tmp);
-            for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];
+            if (m->tp_world > 1) matvec_row_parallel(&L->w2, g, x, m->tp_world, m->tp_w2);
+            else {
+                matvec(&L->w2, g, tmp);
+                for (int i = 0; i < E; i++) x[i] = tmp[i] + x[i];
+            }
         } else {
             matvec(&L->wo, att, ao);                                       /* attn_out */
             matvec(&L->w3, nrm, g);                                        /* FFN reads the SAME normed input (parallel block) */

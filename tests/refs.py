@@ -239,6 +239,15 @@ class OracleModel:
         o.orc_model_set_trace(self.m, ptr(self.trace_layers), ptr(self.trace_attn))
         self.n_past = 0
 
+    def set_tp(self, world):
+        """Switch the restatement to the sharded engine's summation order (oracle/llama_oracle.c: tp_world)."""
+        from ctransformers_b200 import tp_plan
+        sh = tp_plan.plan(self.n_embd, self.n_head, self.n_head_kv, self.n_ff, self.n_vocab, world)
+        wo = (C.c_int * (world + 1))(*([s.attn_k[0] for s in sh] + [sh[-1].attn_k[1]]))
+        w2 = (C.c_int * (world + 1))(*([s.ff[0] for s in sh] + [sh[-1].ff[1]]))
+        self.o.orc_model_set_tp.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        assert self.o.orc_model_set_tp(self.m, world, wo, w2) == 0
+
     def eval(self, tokens, batch_size=8):
         """Same chunking as the reference's LLM::BatchEval (llm.h:40-54): the chunk an attention row belongs to fixes its length."""
         toks = np.asarray(tokens, dtype=np.int32)

@@ -263,3 +263,25 @@ def test_device_sampler_draws_the_reference_tokens(model_dir):
     llm2.eval(prompt)
     same_bits(np.array(llm.logits, np.float32), np.array(llm2.logits, np.float32))
     same_bits(np.array(llm.embeddings, np.float32), np.array(llm2.embeddings, np.float32))
+
+
+def test_lazy_sampling_modes_match_the_eager_engine(model_dir):
+    """A decode loop that never reads llm.logits: greedy calls are answered by the engine's own pick (no kernel), sampled calls by
+    the device sampler with the look-ahead step launched behind it, and switching between the two keeps every token equal to an
+    engine that copies its logits to the host after every eval and samples there (the reference's flow)."""
+    path, ctx = modelcases.build("llama_tiny_q4km", model_dir)
+    a, b = load(path, ctx), load(path, ctx)
+    _ = b.logits                                               # b: eager host views from the start
+    prompt = modelcases.prompt_for("llama_tiny_q4km")
+    a.eval(prompt); b.eval(prompt)
+    greedy = dict(top_k=1, repetition_penalty=1.0)
+    sampled = dict(top_k=40, top_p=0.95, temperature=0.8, repetition_penalty=1.1)
+    plan = [greedy] * 6 + [sampled] * 6 + [greedy] * 4 + [sampled] * 2 + [greedy] * 3 + [dict(top_k=1, repetition_penalty=1.3)] * 3
+    before = a.ctb_llm_device_samples()
+    for i, kw in enumerate(plan):
+        ta, tb = a.sample(seed=i, **kw), b.sample(seed=i, **kw)
+        assert ta == tb, (i, kw)
+        a.eval([ta]); b.eval([tb])
+    assert a.ctb_llm_device_samples() - before >= len(plan) - 2
+    assert a.ctb_llm_speculative_hits() >= 6                   # the greedy stretches ride the look-ahead
+    same_bits(np.array(a.logits, np.float32), np.array(b.logits, np.float32))

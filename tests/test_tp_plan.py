@@ -43,3 +43,42 @@ def test_the_survey_s_13b_example():
 def test_rejects_shapes_that_cannot_be_block_aligned():
     with pytest.raises(ValueError):
         tp_plan.plan(n_embd=4544, n_head=71, n_head_kv=1, n_ff=18176, n_vocab=65024, tp=2)   # true Falcon-7B: 71 heads x 64
+
+
+@pytest.mark.parametrize("shape", [L7, L13, L70ISH, F7], ids=["7b", "13b", "gqa", "falcon-mqa"])
+@pytest.mark.parametrize("tp", [1, 2, 4, 8])
+def test_native_shard_arithmetic_equals_the_plan(lib, shape, tp):
+    """csrc/engine.cu tp_shard (what the engine slices the weights by) == tp_plan.plan, through ctb_tp_shard (no GPU needed)."""
+    import ctypes as C
+    sh = tp_plan.plan(tp=tp, **shape)
+    for r, s in enumerate(sh):
+        out = (C.c_int * 6)()
+        assert lib.ctb_tp_shard(shape["n_embd"], shape["n_head"], shape["n_head_kv"], shape["n_ff"], r, tp, out) == 0
+        assert tuple(out) == (*s.heads, *s.kv_heads, *s.ff)
+
+
+def test_native_shard_rejects_shapes_that_do_not_tile(lib):
+    import ctypes as C
+    out = (C.c_int * 6)()
+    assert lib.ctb_tp_shard(4096, 32, 32, 11000, 0, 2, out) != 0     # n_ff not a multiple of 256
+    assert lib.ctb_tp_shard(4096, 32, 32, 11008, 2, 2, out) != 0     # rank out of range
+    assert lib.ctb_tp_shard(4544, 71, 1, 18176, 0, 2, out) != 0      # true Falcon-7B: head_dim 64 x 71 heads is not whole blocks
+
+
+def test_oracle_tp_mode_only_reorders_the_row_parallel_sums(tmp_models):
+    """oracle/llama_oracle.c tp_world: world 1 is the reference order; world 2 re-associates the fp32 sums of wo / w2 and
+    nothing else, so one layer in, the logits are equal to within fp32 rounding noise (and are NOT required to be identical)."""
+    import numpy as np
+    import modelcases
+    import refs
+    path, ctx = modelcases.build("llama_gqa_q5km", tmp_models)
+    prompt = modelcases.prompt_for("llama_gqa_q5km")[:6]
+    a = refs.OracleModel(str(path), ctx)
+    b = refs.OracleModel(str(path), ctx)
+    b.set_tp(2)
+    la, lb = a.eval(prompt).copy(), b.eval(prompt).copy()
+    rng = float(la.max() - la.min())
+    assert np.abs(la - lb).max() / rng < 5e-2
+    c = refs.OracleModel(str(path), ctx)
+    c.set_tp(1)
+    assert np.array_equal(c.eval(prompt), la)

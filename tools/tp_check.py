@@ -1,0 +1,150 @@
+#!/usr/bin/env python
+"""Tensor-sharded decode (BASELINE configs[4]) on N GPUs of one box: parity, then timing.
+
+    torchrun --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/tp_check.py [--case llama_wide_q4km | --model 13b]
+
+Parity (small cases of tests/modelcases.py): the sharded engine's logits against oracle/llama_oracle.c in its tensor-parallel
+summation mode (tests/refs.py OracleModel.set_tp: per-rank K ranges of wo / w2 as matrices of their own, rank 0 carries the
+residual, ranks added in order).  With 2 ranks the exchange is one commutative fp32 add, so the comparison is BIT-EXACT; with
+more ranks NCCL fixes the order of the adds, so the bound is 1e-3 of the logit range.  Also reported: the distance to the
+unsharded engine (same GPU code, reference summation order) — on random-weight models that distance grows with depth because
+a 1-ulp change flips Q8_K roundings downstream; it is a property of the model, not an error bound.
+Timing (--model 7b/13b, synthetic bench shapes): K greedy steps through eval + sample, wall clock, max over ranks.
+Never hangs on a failed check: every rank reaches the final barrier; the verdict is in the JSON line and the exit code."""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", default=None, help="a tests/modelcases.py llama case: parity against the oracle")
+    ap.add_argument("--model", default=None, choices=["7b", "13b"], help="a bench shape: timing (and distance to the unsharded engine)")
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--parity-steps", type=int, default=6)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from ctransformers_b200 import LLM, Config, synth
+    from ctransformers_b200.tp import tensor_parallel_ticket
+
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")
+    d = Path(os.environ.get("CTB_MODEL_DIR", "/tmp/ctb_models"))
+    d.mkdir(parents=True, exist_ok=True)
+    ok, out = True, {"world": world}
+    if args.case:
+        import modelcases
+        if rank == 0:
+            modelcases.build(args.case, d)
+        dist.barrier()
+        path, ctx = modelcases.build(args.case, d)
+        prompt = modelcases.prompt_for(args.case)[:12]
+        out["case"] = args.case
+    else:
+        shape = {"7b": synth.LLAMA2_7B, "13b": synth.LLAMA2_13B}[args.model or "13b"]
+        path = d / f"llama2-{args.model or '13b'}-shaped.Q4_K_M.synthetic.gguf"
+        if rank == 0 and not path.exists():
+            synth.write_llama(path.with_suffix(".tmp"), shape, "Q4_K_M", seed=0)
+            path.with_suffix(".tmp").rename(path)
+        dist.barrier()
+        ctx = 512
+        prompt = [1] + np.random.default_rng(2).integers(259, shape.n_vocab, 63).tolist()
+        out["model"] = args.model or "13b"
+    cfg = Config(context_length=ctx)
+    t0 = time.time()
+    llm = LLM(str(path), config=cfg, tp=tensor_parallel_ticket())
+    out["load_s"] = round(time.time() - t0, 2)
+    out["launches_per_token"] = int(llm.ctb_llm_launches_per_token())
+
+    def gather(vec):
+        t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.float32))
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return [p.numpy() for p in parts]
+
+    # ---- parity
+    orc = whole = None
+    if rank == 0:
+        whole = LLM(str(path), config=cfg)                     # the unsharded engine on this GPU (bit-exact to the reference)
+        if args.case:
+            import refs
+            orc = refs.OracleModel(str(path), ctx)
+            orc.set_tp(world)
+    n_par = args.parity_steps if args.case else min(args.steps, 8)
+    worst_orc, worst_whole, exact, agree, toks, toks_whole = 0.0, 0.0, True, True, [], []
+    llm.eval(prompt)
+    if whole:
+        whole.eval(prompt)
+    if orc:
+        orc.eval(prompt)
+    for step in range(n_par + 1):
+        lg = np.array(llm.logits, dtype=np.float32)
+        every = gather(lg)
+        agree &= all(np.array_equal(every[0], e) for e in every)
+        t = int(np.argmax(lg))
+        toks.append(t)
+        if whole:
+            ref = np.array(whole.logits, dtype=np.float32)
+            worst_whole = max(worst_whole, float(np.abs(lg - ref).max() / (ref.max() - ref.min())))
+            toks_whole.append(int(np.argmax(ref)))
+        if orc:
+            o = orc.logits
+            exact &= bool(np.array_equal(lg, o))
+            worst_orc = max(worst_orc, float(np.abs(lg - o).max() / (o.max() - o.min())))
+        if step == n_par:
+            break
+        llm.eval([t])
+        if whole:
+            whole.eval([t])      # teacher-forced with the sharded run's token: same context everywhere
+        if orc:
+            orc.eval([t])
+    if rank == 0:
+        out["parity"] = {"steps": n_par + 1, "ranks_agree_bitwise": agree, "vs_unsharded_engine_max_err_over_logit_range": worst_whole,
+                         "greedy_tokens_equal_unsharded": toks == toks_whole}
+        if orc:
+            out["parity"].update({"vs_tp_oracle_bit_exact": exact, "vs_tp_oracle_max_err_over_logit_range": worst_orc})
+            ok &= exact if world == 2 else worst_orc < 1e-3
+        ok &= agree
+    del whole, orc
+    llm.reset()
+
+    # ---- timing: decode after the prompt, through the public API
+    if not args.case:
+        llm.eval(prompt)
+        tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        for _ in range(4):
+            llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            llm.eval([tok]); tok = llm.sample(top_k=1, repetition_penalty=1.0, seed=0)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            out["decode_tokens_per_s_e2e"] = round(args.steps / float(dt[0]), 1)
+            out["last_step_device_ms"] = round(float(llm.ctb_llm_last_eval_ms()), 4)
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        out["ok"] = bool(flag.item())
+        print("TPCHECK " + json.dumps(out), flush=True)
+    dist.barrier()
+    del llm
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() else 1)
+
+
+if __name__ == "__main__":
+    main()
