@@ -454,7 +454,11 @@ void Engine::init(const GGUFFile& g) {
   CTB_CUDA(cudaEventCreateWithFlags(&ev_pick_, cudaEventDisableTiming));
   CTB_CUDA(matvec_set_smem_limit(MV_SMEM_LIMIT));
   CTB_CUDA(cudaFuncSetAttribute(k_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes(hp_.n_ctx, hp_.head_dim())));
+  if (tp_.world > 1) tp_setup_peer();
   build_ops();
+  if (tp_peer_)
+    for (const StepOp& op : ops_)
+      if (op.ph.kind == PH_MATVEC && !op.stream) throw std::runtime_error("tensor parallel (fused exchange): every mat-vec must run in the step kernel (K-quant weights)");
   CTB_CUDA(cudaDeviceSynchronize());
   build_graphs();
 }
@@ -470,6 +474,11 @@ void Engine::release() {
   if (h_state_) cudaFreeHost(h_state_);
   if (h_tokens_out_) cudaFreeHost(h_tokens_out_);
   if (d_tokens_out_) cudaFree(d_tokens_out_);
+  for (int r = 0; r < 8; r++)
+    if (xc_ll_[r] && r != tp_.rank) cudaIpcCloseMemHandle(xc_ll_[r]);
+  if (xc_region_) cudaFree(xc_region_);
+  xc_region_ = nullptr;
+  for (int r = 0; r < 8; r++) xc_ll_[r] = nullptr;
   if (arena_) cudaFree(arena_);
   if (h_spec_tok_) cudaFreeHost(h_spec_tok_);
   if (h_dbg_) cudaFreeHost(h_dbg_);
@@ -521,16 +530,77 @@ void Engine::tp_all_reduce(float* buf, int n) {
   nccl.check(nccl.AllReduce(buf, buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)tp_.comm, stream_), "all-reduce");
 }
 
+// Fused exchange set-up: allocate this rank's region, hand its CUDA IPC handle to the peers (the NCCL communicator carries the 64
+// bytes), map theirs.  All-or-nothing across ranks: if any rank cannot map a peer, every rank stays on the NCCL all-reduce path.
+void Engine::tp_setup_peer() {
+  const NcclApi& nccl = NcclApi::get();
+  const int W = tp_.world;
+  const size_t bytes = align_up((size_t)2 * W * hp_.n_embd * sizeof(uint2), 256);
+  int ok = 1;
+  cudaIpcMemHandle_t mine;
+  std::vector<cudaIpcMemHandle_t> all(W);
+  uint8_t* d_h = (uint8_t*)alloc(sizeof(cudaIpcMemHandle_t) * W + 16, 256);
+  int* d_ok = (int*)(d_h + sizeof(cudaIpcMemHandle_t) * W);
+  if (W > XC_MAX_WORLD || getenv("CTB_TP_NCCL")) ok = 0;
+  if (ok && cudaMalloc(&xc_region_, bytes) != cudaSuccess) { xc_region_ = nullptr; ok = 0; }
+  if (ok) {
+    CTB_CUDA(cudaMemset(xc_region_, 0, bytes));
+    if (cudaIpcGetMemHandle(&mine, xc_region_) != cudaSuccess) ok = 0;
+  }
+  if (!ok) memset(&mine, 0, sizeof(mine));
+  cudaGetLastError();
+  CTB_CUDA(cudaMemcpy(d_h + sizeof(mine) * tp_.rank, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  nccl.check(nccl.AllGather(d_h + sizeof(mine) * tp_.rank, d_h, sizeof(mine), ncclChar, (ncclComm_t)tp_.comm, stream_), "all-gather of the IPC handles");
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  CTB_CUDA(cudaMemcpy(all.data(), d_h, sizeof(mine) * W, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < W && ok; r++) {
+    void* base = xc_region_;
+    if (r != tp_.rank && cudaIpcOpenMemHandle(&base, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+    xc_ll_[r] = (uint2*)base;
+  }
+  CTB_CUDA(cudaMemcpy(d_ok, &ok, 4, cudaMemcpyHostToDevice));
+  nccl.check(nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, (ncclComm_t)tp_.comm, stream_), "all-reduce");
+  CTB_CUDA(cudaStreamSynchronize(stream_));
+  CTB_CUDA(cudaMemcpy(&ok, d_ok, 4, cudaMemcpyDeviceToHost));
+  tp_peer_ = ok != 0;
+  if (!tp_peer_ && tp_.rank == 0 && !getenv("CTB_TP_NCCL"))
+    fprintf(stderr, "ctransformers-b200: peer memory between the ranks is not available; the tensor-parallel exchange uses NCCL all-reduce\n");
+}
+
 void Engine::build_ops() {
   // nh_ / nkv_ / nff_ are this rank's share (the whole model without tensor parallelism)
   const int n_embd = hp_.n_embd, hd = hp_.head_dim(), n_kv = nkv_, gqa = nkv_ * hp_.head_dim(), qw = nh_ * hp_.head_dim();
   const bool tp = tp_.world > 1;
   const bool tp_lead = tp_.rank == 0;   // the rank whose partial sum carries the residual
+  int n_xchg = 0;                       // exchanges so far in the program
+  bool xchg_due = false;                // fused mode: the next mat-vec phase consumes the exchange the last one produced
+  float* x_sum_into = nullptr;
+  auto fill_xc = [&](XchgParams& xc, int role) {
+    xc.world = tp_.world; xc.rank = tp_.rank; xc.index = n_xchg; xc.n = n_embd; xc.role = role;
+    for (int r = 0; r < tp_.world; r++) xc.ll[r] = xc_ll_[r];
+  };
   auto push_xchg = [&](float* buf) {    // all-reduce of a row-parallel mat-vec's partial sums (+ the residual, once)
+    if (tp_peer_) {                     // fused: that phase's epilogue sends its rows to every rank; the next phase sums them into buf
+      fill_xc(ops_.back().ph.xc, 2);
+      xchg_due = true;
+      x_sum_into = buf;
+      return;
+    }
     StepOp op{};
     op.ph.kind = PH_XCHG;
     op.ph.em.out = buf; op.ph.em.K = n_embd;
     ops_.push_back(op);
+  };
+  auto take_input = [&](MVParams& p) {   // fused: the input is the sum of the ranks' vectors of the exchange that is due
+    if (!xchg_due) return;
+    p.x = (const float*)xc_ll_[tp_.rank]; p.x_mode = 2; p.x_parts = tp_.world; p.x_stride = n_embd; p.sum_out = x_sum_into;
+  };
+  auto mark_exchange = [&](size_t first_op) {
+    if (!xchg_due) return;
+    if (ops_.size() != first_op + 1) throw std::runtime_error("tensor parallel (fused exchange): the consumer of an exchange must be one mat-vec phase");
+    fill_xc(ops_[first_op].ph.xc, 1);
+    n_xchg++;
+    xchg_due = false; x_sum_into = nullptr;
   };
   const float kq_scale = 1.0f / sqrtf((float)n_embd / (float)hp_.n_head);
   ops_.clear();
@@ -562,6 +632,8 @@ void Engine::build_ops() {
       {  // attention_norm + wq/wk/wv
         MVParams p{};
         p.x = x; p.norm_w = L.attn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+        const size_t first_op = ops_.size();
+        take_input(p);
         const DevMat* ws[3] = {&L.wq, &L.wk, &L.wv};
         float* outs[3] = {q, k, v};
         bool done[3] = {false, false, false};
@@ -573,6 +645,7 @@ void Engine::build_ops() {
             if (!done[j] && act_format_for(ws[j]->type) == p.act) { p.seg[p.nseg++] = seg(*ws[j], outs[j]); done[j] = true; }
           push_matvec(p, MVK_QKV);
         }
+        mark_exchange(first_op);
       }
       push_attn();
       {  // wo + residual
@@ -586,9 +659,12 @@ void Engine::build_ops() {
          // where ffn_down stages its input
         MVParams p{};
         p.x = y; p.norm_w = L.ffn_norm; p.norm_mode = NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+        const size_t first_op = ops_.size();
+        take_input(p);
         p.act = act_format_for(L.w1.type); p.nseg = 2;
         p.seg[0] = seg(L.w1, ffn_, EPI_SILU); p.seg[1] = seg(L.w3, ffn2_);
         push_matvec(p, MVK_UP);
+        mark_exchange(first_op);
       }
       {  // w2 on silu(gate)*up, + residual
         MVParams p{};
@@ -640,9 +716,13 @@ void Engine::build_ops() {
   {
     MVParams p{};
     p.x = x; p.norm_w = out_norm_; p.norm_b = out_norm_b_; p.norm_mode = hp_.falcon ? NORM_LAYER : NORM_RMS; p.eps = hp_.eps; p.K = n_embd;
+    const size_t first_op = ops_.size();
+    take_input(p);
     p.norm_out = d_embd_; p.act = act_format_for(output_.type); p.nseg = 1;
     p.seg[0] = seg(output_, d_logits_);
     push_matvec(p, MVK_OUT);
+    mark_exchange(first_op);
+
   }
   {
     StepOp op{};
@@ -759,6 +839,7 @@ void Engine::mark(int kind) {
 // One eager decode step, one kernel per op (un-fused), a CUDA event around every kernel: the kernel classes' share of a step.
 int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_by_kind[4]) {
   DeviceGuard dev_guard(device_);
+  if (tp_.world > 1) throw std::runtime_error("not available in tensor-parallel mode (every rank must run the same launches)");
   spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   if (h_state_cap_ < 1) { h_state_cap_ = 512; CTB_CUDA(cudaMallocHost(&h_state_, (size_t)h_state_cap_ * 16)); }
   h_state_[0] = token; h_state_[1] = n_past; h_state_[2] = 0; h_state_[3] = n_past + 1;
@@ -787,6 +868,7 @@ int Engine::profile_step(int token, int n_past, double ms_by_kind[4], int count_
 // keep the mat-vecs of kind k (0 = all).  with_attn: keep the attention phases too (times the dependency chain as it is).
 double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
   if (!mask) mask = ~0u;
+  if (tp_.world > 1) throw std::runtime_error("not available in tensor-parallel mode (every rank must run the same launches)");
   spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   DeviceGuard dev_guard(device_);
   std::vector<StepOp> sel;
@@ -827,6 +909,7 @@ double Engine::time_matvec_only(int reps, long* launches, unsigned mask) {
 // first weight item ready, phase done + 4 stamps of the grid barrier in front of the phase).  out: n_phases x {kind, mvk} then n_phases x n_cta x 8 stamps; returns n_phases or -(words needed).
 long Engine::trace_step(int token, int n_past, unsigned long long* out, long cap_words) {
   DeviceGuard dev_guard(device_);
+  if (tp_.world > 1) throw std::runtime_error("not available in tensor-parallel mode (every rank must run the same launches)");
   spec_pending_ = false; spec_deferred_ = false; spec_pos_ = -1; spec_streak_ = 0;
   const int n = n_body_ + 1;
   for (int i = 0; i < n; i++)
@@ -875,7 +958,8 @@ void Engine::build_graphs() {
   auto capture = [&](bool logits, bool greedy) {
     cudaGraph_t g;
     CTB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-    enqueue_ops(ops_, d_prog_, d_bounds_, n_body_ + (logits ? 1 : 0) + (greedy ? 1 : 0));
+    // (fused tensor-parallel exchange: the head phase consumes the last layer's exchange, so every program contains it)
+    enqueue_ops(ops_, d_prog_, d_bounds_, n_body_ + (logits || tp_peer_ ? 1 : 0) + (greedy ? 1 : 0));
     CTB_CUDA(cudaStreamEndCapture(cap, &g));
     cudaGraphExec_t ex;
     CTB_CUDA(cudaGraphInstantiate(&ex, g, 0));

@@ -97,6 +97,11 @@ class Engine {
   TPShard tp_;
   int nh_ = 0, nkv_ = 0, nff_ = 0;   // this rank's query heads, KV heads and n_ff slice (the whole model when world == 1)
   void tp_all_reduce(float* buf, int n);
+  // fused exchange (stream.cuh: XchgParams): this rank's region  uint2 ll[2][world][n_embd]  and every peer's, IPC-mapped
+  bool tp_peer_ = false;
+  uint8_t* xc_region_ = nullptr;
+  uint2* xc_ll_[8] = {nullptr};
+  void tp_setup_peer();
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   bool own_stream_ = true;

@@ -30,6 +30,21 @@ constexpr int MV_MAX_SEG = 3;
 enum : int { NORM_NONE = 0, NORM_RMS = 1, NORM_LAYER = 2 };
 enum : int { EPI_STORE = 0, EPI_ADD = 1, EPI_GELU = 2, EPI_ADD2 = 3, EPI_SILU = 4 };   // GELU / SILU: the reference's fp16-table activation of the row value
 
+// Every spin in the persistent kernels is bounded: a wait that lasts longer than ST_WATCHDOG_NS writes {code, CTA, aux} into
+// host-mapped memory and traps — a protocol bug then ends as a launch failure with a message, not as a hung GPU.
+#ifndef ST_WATCHDOG_NS
+#define ST_WATCHDOG_NS 4000000000ull
+#endif
+static __device__ int* g_st_dbg = nullptr;   // set by the host (st_set_debug_words): 4 ints of mapped pinned host memory, or null
+static __device__ __noinline__ void st_fail(int code, int aux) {
+  int* d = g_st_dbg;
+  if (d) { d[0] = code; d[1] = (int)blockIdx.x; d[2] = aux; d[3] = (int)threadIdx.x; __threadfence_system(); }
+  __trap();
+}
+#ifndef XC_WATCHDOG_NS
+#define XC_WATCHDOG_NS 30000000000ull   // a peer rank may start its launch late (host jitter): 30 s
+#endif
+
 struct MVSeg {
   DevMat w;
   float* out;          // [M]
@@ -42,6 +57,12 @@ struct MVParams {
   const float* x;        // [K] f32 input
   const float* x2;       // x_mode 1: second operand
   int x_mode;            // 0: x;  1: x * x2 (ggml_mul of silu(gate) and up, llama.cpp:2438-2443; the SiLU table is applied by the gate rows' epilogue)
+                         // 2: x is a uint2 array of {float bits, exchange number} elements (stream.cuh: XchgParams): the input is
+                         //    part[0] + part[1] + ... + part[x_parts-1], parts x_stride elements apart, added in that order
+                         //    (tensor-parallel partial sums of a row-parallel mat-vec, one per rank; rank 0's carries the
+                         //    residual); an element is valid once its number equals the exchange number the caller passes
+  int x_parts, x_stride;
+  float* sum_out;        // x_mode 2, optional [K]: CTA 0 writes the summed vector (the residual stream of the next block)
   const float* norm_w;   // [K] or null
   const float* norm_b;   // [K] or null (LayerNorm bias)
   float* norm_out;       // optional [K]: CTA 0 writes the normalised vector (result_norm / embeddings)
@@ -134,7 +155,43 @@ __device__ __forceinline__ uint32_t pack4(const int* q) {
 // 16 consecutive input elements with the producer's activation applied: the reference's fp16-table SiLU (ggml.c:3625-3632)
 // times the up projection, or the fp16-table GELU (ggml.c:3568-3575) — fused here instead of in the producing kernel so that
 // gate and up can be two independent row sets there.
-__device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid, float (&v)[16]) {
+// 16 consecutive {value, number} elements of one rank's partial vector; spins until all carry `epoch`
+__device__ __forceinline__ void load16_ll(const uint2* p, unsigned epoch, float (&u)[16]) {
+  uint4 q[8];
+  unsigned long long t0 = 0;
+  for (;;) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[j].x), "=r"(q[j].y), "=r"(q[j].z), "=r"(q[j].w) : "l"(p + 2 * j) : "memory");
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) ok &= q[j].y == epoch && q[j].w == epoch;
+    if (ok) break;
+    if (!t0) t0 = globaltimer_ns();
+    else if (globaltimer_ns() - t0 > XC_WATCHDOG_NS) st_fail(10, (int)epoch);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) { u[2 * j] = __uint_as_float(q[j].x); u[2 * j + 1] = __uint_as_float(q[j].z); }
+}
+
+__device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid, float (&v)[16], unsigned epoch = 0) {
+  if (xs.x_mode == 2) {   // (K is a multiple of 256 and base of 16: a thread's 16 elements are all valid or all past the end)
+    if (valid <= 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = 0.f;
+      return;
+    }
+    const uint2* ll = (const uint2*)xs.x + (size_t)(epoch & 1u) * xs.x_parts * xs.x_stride;   // the parity half this exchange uses
+    load16_ll(ll + base, epoch, v);
+    for (int r = 1; r < xs.x_parts; r++) {
+      float u[16];
+      load16_ll(ll + (size_t)r * xs.x_stride + base, epoch, u);
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = __fadd_rn(v[e], u[e]);
+    }
+    return;
+  }
   load16<true>(xs.x + base, valid, v);
   if (xs.x_mode == 1) {          // x = silu_table(gate) (applied once, where the gate row was produced); input = x * up (ggml_mul)
     float u[16];
@@ -156,13 +213,13 @@ __device__ __forceinline__ void preload_norm(NormPre& np, const float* nw, const
 // The first NT threads of the CTA must call (named barrier BAR); each owns 16 consecutive elements per pass.
 template <int NT, int BAR>
 __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormPre& np, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
-                                                  int K, int act, uint8_t* smem, double* red, bool write_norm) {
+                                                  int K, int act, uint8_t* smem, double* red, bool write_norm, unsigned epoch = 0) {
   const int t = threadIdx.x, lane = t & 31;
   const int passes = (K + NT * 16 - 1) / (NT * 16);
   // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
   float mean = 0.f, scale = 1.f;
   float v0[16];                          // pass 0's x stays in registers
-  load16x(xs, t * 16, K - t * 16, v0);
+  load16x(xs, t * 16, K - t * 16, v0, epoch);
   if (norm_mode == NORM_RMS) {
     double ss = 0.0;
     for (int ps = 0; ps < passes; ps++) {
@@ -172,7 +229,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       if (ps == 0) {
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = v0[e];
-      } else load16x(xs, base, K - base, v);
+      } else load16x(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) ss += (double)__fmul_rn(v[e], v[e]);
     }
@@ -185,7 +242,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       const int base = (ps * NT + t) * 16;
       if ((base & ~511) >= K) continue;
       float v[16];
-      load16x(xs, base, K - base, v);
+      load16x(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) s1 += (double)v[e];
     }
@@ -196,7 +253,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       const int base = (ps * NT + t) * 16;
       if ((base & ~511) >= K) continue;
       float v[16];
-      load16x(xs, base, K - base, v);
+      load16x(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) { const float d = (base + e < K) ? __fsub_rn(v[e], mean) : 0.f; s2 += (double)__fmul_rn(d, d); }
     }
@@ -217,7 +274,11 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     if (ps == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = v0[e];
-    } else load16x(xs, base, valid, v);
+    } else load16x(xs, base, valid, v, epoch);
+    if (write_norm && xs.x_mode == 2 && xs.sum_out && valid > 0) {
+#pragma unroll
+      for (int e = 0; e < 16; e++) if (e < valid) xs.sum_out[base + e] = v[e];
+    }
     if (norm_mode != NORM_NONE) {
       float w[16], bb[16];
       if (ps == 0) {

@@ -130,17 +130,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(st_smem(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Every spin in the persistent kernels is bounded: a wait that lasts longer than ST_WATCHDOG_NS writes {code, CTA, aux} into
-// host-mapped memory and traps — a protocol bug then ends as a launch failure with a message, not as a hung GPU.
-#ifndef ST_WATCHDOG_NS
-#define ST_WATCHDOG_NS 4000000000ull
-#endif
-static __device__ int* g_st_dbg = nullptr;   // set by the host (st_set_debug_words): 4 ints of mapped pinned host memory, or null
-static __device__ __noinline__ void st_fail(int code, int aux) {
-  int* d = g_st_dbg;
-  if (d) { d[0] = code; d[1] = (int)blockIdx.x; d[2] = aux; d[3] = (int)threadIdx.x; __threadfence_system(); }
-  __trap();
-}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int code = 1, int aux = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const unsigned long long t0 = globaltimer_ns();
@@ -172,6 +161,8 @@ struct StAct {
   const uint32_t* pairs;
   const int* cneg;
   const int8_t* zero;   // 256 zero bytes (what the off-diagonal lanes of the mma B operand read)
+  const struct XchgParams* xc;   // non-null: the phase produces a tensor-parallel exchange (rows go to every rank's ll slots)
+  unsigned epoch;
 };
 __host__ __device__ inline size_t st_off_pairs(int K) { return ((((size_t)K + 15) & ~(size_t)15) + q8k_d_bytes(K) + (size_t)(K / 16) * 2 + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t st_act_bytes(int K, bool q6) { return st_off_pairs(K) + (size_t)(K / 256) * 16 + (q6 ? (size_t)K : 0) + 256 + 16; }
@@ -464,7 +455,18 @@ __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_ba
   }
   if (t < 2) {
     const int row = row0 + g + 8 * t;
-    if (row < sg.w.M) store_epilogue(sg, p, row, t ? out[1] : out[0]);
+    if (row < sg.w.M) {
+      if (a.xc) {   // tensor-parallel partial sum: {value (+ residual on the rank that carries it), exchange number} to every rank
+        float v = t ? out[1] : out[0];
+        if (sg.epi == EPI_ADD) v = __fadd_rn(v, __ldcg(sg.res + row));
+        const XchgParams& xc = *a.xc;
+        const size_t at = ((size_t)(a.epoch & 1u) * xc.world + xc.rank) * xc.n + row;
+        for (int r = 0; r < xc.world; r++)
+          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(xc.ll[r] + at), "r"(__float_as_uint(v)), "r"(a.epoch) : "memory");
+      } else {
+        store_epilogue(sg, p, row, t ? out[1] : out[0]);
+      }
+    }
   }
 }
 
@@ -509,7 +511,22 @@ struct TileSpace {
 // ---------------------------------------------------------------------------------------------
 // Phases of a step
 enum : int { PH_MATVEC = 0, PH_ATTN = 1, PH_EMBED = 2, PH_PICK = 3,
-              PH_XCHG = 4 };   // PH_XCHG: host-side schedule entry only (tensor-parallel all-reduce between two launches), never a kernel phase
+              PH_XCHG = 4 };   // PH_XCHG: host-side schedule entry only (tensor-parallel NCCL all-reduce between two launches), never a kernel phase
+// Tensor-parallel exchange fused into the step (peer memory over NVLink; no kernel boundary, no NCCL call, no fence).  Every rank
+// owns a region  uint2 ll[2][world][n]  that all ranks have mapped (CUDA IPC); an element is {float bits, exchange number} and is
+// always written with ONE 8-byte store, so a reader that sees the right exchange number sees the value that came with it (the
+// "LL" idea of NCCL's low-latency protocol).  The row-parallel phase (role 2) stores every finished output row of this rank,
+// residual included on rank 0, into ll[parity][rank][row] of EVERY rank straight from its epilogue; the next mat-vec phase
+// (role 1) stages  x = ll[parity][0] + ll[parity][1] + ...  (rank order: every rank forms the same bits), spinning on elements
+// whose number is not there yet.  The copies ride under the local grid barrier, so an exchange costs about one NVLink hop.
+// Two parities suffice: a rank can produce exchange k+2 only after it has consumed k+1, which its peers produce after they
+// have finished reading k.
+constexpr int XC_MAX_WORLD = 8;
+struct XchgParams {
+  int world, rank, index, n;           // index: number of this exchange inside the program (0-based); n: elements per vector
+  int role;                            // 0 none, 1 this phase consumes the exchange (sums it while staging), 2 it produces it
+  uint2* ll[XC_MAX_WORLD];             // region base of every rank as mapped here
+};
 struct EmbedParams { const uint8_t* table; size_t row_bytes; const int* tokens; float* out; int type, K, n_vocab; };
 struct PickParams { const float* logits; int* state; int* out_tokens; int n; };
 struct alignas(16) Phase {
@@ -520,13 +537,14 @@ struct alignas(16) Phase {
   AttnParams at;    // PH_ATTN
   EmbedParams em;   // PH_EMBED
   PickParams pk;    // PH_PICK
+  XchgParams xc;    // PH_MATVEC with xc.world > 1: the tensor-parallel exchange in front of this phase's staging
 };
 
 struct StepArgs {
   const Phase* prog;
   int n_phases;
   int n_slots;
-  unsigned* sync;   // [0] grid-barrier arrivals, [1] finished CTAs (the last one resets both)
+  unsigned* sync;   // [0] grid-barrier arrivals, [1] finished CTAs (the last one resets both), [2] tensor-parallel exchanges done so far
   const int* bounds;   // [n_phases][grid + 1]: first tile of every CTA per mat-vec phase (TileSpace::boundary, computed once on the host)
   unsigned long long* trace;   // optional: per phase and CTA 8 globaltimer stamps {phase starts, input staged, first item ready, phase done,
                                //           previous phase left (barrier entered), arrive issued, all arrived seen, acquire fence done}
@@ -822,11 +840,15 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
 
 // Consumer side of one mat-vec phase.  `seq` is the running item number (identical in every warp and in the producer).
 __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& np, uint8_t* ring, uint8_t* act_smem, double* red, uint64_t* full_bar, uint64_t* empty_bar,
-                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, const int* tb, unsigned long long* tr) {
+                                                float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, const int* tb, unsigned long long* tr,
+                                                unsigned xc_base) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0);
-  const StAct a = st_act_extras<ST_NT, ST_BAR>(act_smem, p.K, ph.q6 != 0);
+  const unsigned epoch = xc_base + (unsigned)ph.xc.index + 1u;   // number of the exchange this phase consumes / produces (if any)
+  stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0, epoch);
+  StAct a = st_act_extras<ST_NT, ST_BAR>(act_smem, p.K, ph.q6 != 0);
+  a.xc = ph.xc.role == 2 ? &ph.xc : nullptr;
+  a.epoch = epoch;
   if (tr && threadIdx.x == 0) tr[1] = globaltimer_ns();
   bool first_item = tr != nullptr && threadIdx.x == 0;
   TileSpace ts;
@@ -929,6 +951,8 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
   }
   const unsigned G = gridDim.x;
   uint32_t seq = 0;
+  const unsigned xc_base = ld_relaxed_u32(args.sync + 2);   // (changes only after every CTA has left its last barrier)
+  unsigned xc_done = 0;
   // descriptor of phase ip -> ph_s[ip & 1]; issued one phase ahead so that no global round trip sits on the phase boundary
   auto fetch_phase = [&](int ip) {
     if (ip >= args.n_phases) return;
@@ -969,9 +993,10 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     NormPre np;
     if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);
     if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
+    if (ph.kind == PH_MATVEC && ph.xc.role == 1) xc_done++;
     if (ph.kind == PH_MATVEC) {
       // (the tile bounds were written by threads 0/1 above; the barriers inside the activation staging order them)
-      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)(args.n_slots / ST_W), seq, &tb_s[ip & 1][0], tr);
+      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)(args.n_slots / ST_W), seq, &tb_s[ip & 1][0], tr, xc_base);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
       if (ph.q6) {
@@ -1007,6 +1032,7 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     if (atomicAdd(args.sync + 1, 1u) == G - 1) {   // every CTA is past its last barrier: re-arm for the next launch
       args.sync[0] = 0u;
       args.sync[1] = 0u;
+      args.sync[2] = xc_base + xc_done;
       __threadfence();
     }
   }

@@ -14,6 +14,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 
   static NcclApi& get() {
@@ -39,6 +40,7 @@ struct NcclApi {
     a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
     a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
     a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
     a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
     return a;
   }

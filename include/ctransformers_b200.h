@@ -74,8 +74,8 @@ double ctb_llm_load_ms(LLM* llm);
  * it has no multi-GPU path).  One process per GPU: rank 0 calls ctb_tp_unique_id (128 bytes, a ncclUniqueId) and hands the
  * bytes to the other ranks by any host channel; every rank then calls ctb_llm_create_tp.  Each rank keeps its query heads
  * (with their KV heads) and its n_ff slice, cut on 256-element block boundaries (ctb_tp_shard reports the ranges:
- * head0, head1, kv0, kv1, ff0, ff1), and the step exchanges two n_embd-float all-reduces per layer over NCCL.  llama graph
- * only; every rank must make the same calls in the same order and ends up with the same logits. */
+ * head0, head1, kv0, kv1, ff0, ff1), and the step sums two n_embd-float vectors per layer across the ranks — inside the step
+ * kernel over NVLink peer memory (CUDA IPC), or with NCCL all-reduce between launches (CTB_TP_NCCL=1).  llama graph only; every rank must make the same calls in the same order and ends up with the same logits. */
 int ctb_tp_unique_id(void* out, int cap);                     /* bytes written (128), or -needed */
 LLM* ctb_llm_create_tp(const char* model_path, const char* model_type, const ctransformers_config config, int rank, int world,
                        const void* unique_id);

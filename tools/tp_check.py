@@ -5,8 +5,9 @@
 
 Parity (small cases of tests/modelcases.py): the sharded engine's logits against oracle/llama_oracle.c in its tensor-parallel
 summation mode (tests/refs.py OracleModel.set_tp: per-rank K ranges of wo / w2 as matrices of their own, rank 0 carries the
-residual, ranks added in order).  With 2 ranks the exchange is one commutative fp32 add, so the comparison is BIT-EXACT; with
-more ranks NCCL fixes the order of the adds, so the bound is 1e-3 of the logit range.  Also reported: the distance to the
+residual, ranks added in order).  The fused exchange (default) adds the ranks in rank order, so the comparison is BIT-EXACT for
+any world size; on the NCCL path (CTB_TP_NCCL=1) it is bit-exact with 2 ranks (one commutative add) and bounded by 1e-3 of
+the logit range with more (NCCL fixes the order of the adds).  Also reported: the distance to the
 unsharded engine (same GPU code, reference summation order) — on random-weight models that distance grows with depth because
 a 1-ulp change flips Q8_K roundings downstream; it is a property of the model, not an error bound.
 Timing (--model 7b/13b, synthetic bench shapes): K greedy steps through eval + sample, wall clock, max over ranks.
@@ -114,7 +115,8 @@ def main():
                          "greedy_tokens_equal_unsharded": toks == toks_whole}
         if orc:
             out["parity"].update({"vs_tp_oracle_bit_exact": exact, "vs_tp_oracle_max_err_over_logit_range": worst_orc})
-            ok &= exact if world == 2 else worst_orc < 1e-3
+            fused = out["launches_per_token"] == 1          # the in-kernel exchange adds the ranks in rank order, like the oracle
+            ok &= exact if (world == 2 or fused) else worst_orc < 1e-3
         ok &= agree
     del whole, orc
     llm.reset()
