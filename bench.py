@@ -43,10 +43,10 @@ REF_SO = ROOT / "oracle" / "_ref" / "libctransformers_ref.so"
 # --workload: the default is the BASELINE.json headline (configs[1]); "falcon7b" is configs[3] (not a driver bench line)
 WORKLOADS = {
     "llama2-7b": dict(file="llama2-7b-shaped.Q4_K_M.synthetic.gguf", arch="llama", shape="LLAMA2_7B", ftype="Q4_K_M", lo=259,
-                      metric="decode tokens/s Llama-2-7B Q4_K_M b=1", dtype="int8 (q4_K/q6_K weights x q8_K activations, dp4a), fp32 combine",
+                      metric="decode tokens/s Llama-2-7B Q4_K_M b=1", dtype="int8 (q4_K/q6_K weights x q8_K activations, mma.sync u8 x s8 -> exact int32), fp32 combine in the reference's order",
                       name="Llama-2-7B-shaped Q4_K_M GGUF"),
     "falcon7b": dict(file="falcon-7b-shaped.Q5_K_M.synthetic.gguf", arch="falcon", shape="FALCON_7B_SHAPED", ftype="Q5_K_M", lo=0,
-                     metric="decode tokens/s Falcon-7B Q5_K_M b=1", dtype="int8 (q5_K/q6_K/q8_0 weights x q8_K/q8_0 activations, dp4a), fp32 combine",
+                     metric="decode tokens/s Falcon-7B Q5_K_M b=1", dtype="int8 (q5_K/q6_K weights x q8_K activations, mma.sync u8 x s8 -> exact int32), fp32 combine in the reference's order",
                      name="Falcon-7B-shaped (n_embd 4608, multi-query) Q5_K_M GGUF"),
 }
 # configs[2]: prompt ingestion of the same model (the batched kernel of csrc/prefill.cuh); a separate bench line, not the driver's

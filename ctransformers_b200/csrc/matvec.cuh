@@ -266,6 +266,9 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
   const size_t off = ((size_t)K + 15) & ~(size_t)15;
   float* dd = (float*)(smem + off);
   int16_t* bs = (int16_t*)(smem + off + q8k_d_bytes(K));
+#ifndef CTB_STAGE_SERIAL
+  float vn[16];                             // the next pass's x, requested before this pass is processed (L2 round trips overlap)
+#endif
   for (int ps = 0; ps < passes; ps++) {
     const int base = (ps * NT + t) * 16;
     const int valid = K - base;
@@ -274,7 +277,20 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     if (ps == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = v0[e];
-    } else load16x(xs, base, valid, v, epoch);
+    } else {
+#ifndef CTB_STAGE_SERIAL
+#pragma unroll
+      for (int e = 0; e < 16; e++) v[e] = vn[e];
+#else
+      load16x(xs, base, valid, v, epoch);
+#endif
+    }
+#ifndef CTB_STAGE_SERIAL
+    {
+      const int nbase = ((ps + 1) * NT + t) * 16;
+      if (ps + 1 < passes && (nbase & ~511) < K) load16x(xs, nbase, K - nbase, vn, epoch);
+    }
+#endif
     if (write_norm && xs.x_mode == 2 && xs.sum_out && valid > 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) if (e < valid) xs.sum_out[base + e] = v[e];

@@ -373,6 +373,7 @@ int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int
     max_items = std::max(max_items, items);
   }
   meta[0] = n_sm; meta[1] = ST_SLOT; meta[2] = ST_MAXT; meta[3] = ts.ntiles; meta[4] = ST_W; meta[5] = ST_ROWS; meta[6] = (int)max_items;
+  meta[7] = st_chunk_blocks(GT_Q4_K) | (st_chunk_blocks(GT_Q5_K) << 8) | (st_chunk_blocks(GT_Q6_K) << 16);
   return 0;
 }
 

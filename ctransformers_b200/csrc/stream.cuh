@@ -52,7 +52,17 @@ constexpr int ST_STATE = 6;             // floats of fold state per thread: 4 AV
 
 __host__ __device__ inline int st_row_block_bytes(int type) { return type == GT_Q4_K ? 144 : (type == GT_Q5_K ? 176 : 210); }
 __host__ __device__ inline int st_block_bytes(int type) { return ST_ROWS * st_row_block_bytes(type); }   // 2304 / 2816 / 3360
-__host__ __device__ inline int st_chunk_blocks(int type) { return type == GT_Q4_K ? 4 : (type == GT_Q5_K ? 3 : 2); }
+#ifndef CTB_CHUNK_Q4
+#define CTB_CHUNK_Q4 4
+#endif
+#ifndef CTB_CHUNK_Q5
+#define CTB_CHUNK_Q5 3
+#endif
+#ifndef CTB_CHUNK_Q6
+#define CTB_CHUNK_Q6 2
+#endif
+static_assert(CTB_CHUNK_Q4 * 2304 <= ST_SLOT && CTB_CHUNK_Q5 * 2816 <= ST_SLOT && CTB_CHUNK_Q6 * 3360 <= ST_SLOT, "a work item must fit one ring slot");
+__host__ __device__ inline int st_chunk_blocks(int type) { return type == GT_Q4_K ? CTB_CHUNK_Q4 : (type == GT_Q5_K ? CTB_CHUNK_Q5 : CTB_CHUNK_Q6); }
 __host__ __device__ inline int st_tile_cost(int type) { return type == GT_Q6_K ? 105 : (type == GT_Q5_K ? 88 : 72); }   // bytes per row-block / 2
 __host__ __device__ inline size_t st_matrix_bytes(int type, int M, int nb) { return (size_t)((M + ST_ROWS - 1) / ST_ROWS) * nb * st_block_bytes(type); }
 
@@ -371,9 +381,9 @@ __device__ __forceinline__ void block_terms<GT_Q6_K>(const uint8_t* blk, int b, 
 }
 
 template <int TYPE> struct StTraits;
-template <> struct StTraits<GT_Q4_K> { static constexpr int KB = 4, BB = 2304, NM = 2; };
-template <> struct StTraits<GT_Q5_K> { static constexpr int KB = 3, BB = 2816, NM = 1; };
-template <> struct StTraits<GT_Q6_K> { static constexpr int KB = 2, BB = 3360, NM = 0; };
+template <> struct StTraits<GT_Q4_K> { static constexpr int KB = CTB_CHUNK_Q4, BB = 2304, NM = 2; };
+template <> struct StTraits<GT_Q5_K> { static constexpr int KB = CTB_CHUNK_Q5, BB = 2816, NM = 1; };
+template <> struct StTraits<GT_Q6_K> { static constexpr int KB = CTB_CHUNK_Q6, BB = 3360, NM = 0; };
 
 // One work item: blocks [b0, b0 + nblk) of the 16-row tile whose pieces lie in `slot`.  Integer work first (the slot is
 // released as soon as the last weight word has been read), then the ordered fp32 fold: state in from the mailbox unless this
@@ -571,7 +581,7 @@ __device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParam
     ti.seg = ts.locate(tl);
     ti.til = tl;
     ti.type = ti.seg == 0 ? p.seg[0].w.type : (ti.seg == 1 ? p.seg[1].w.type : p.seg[2].w.type);
-    ti.nch = ti.type == GT_Q4_K ? (nb + 3) >> 2 : (ti.type == GT_Q5_K ? (nb + 2) / 3 : (nb + 1) >> 1);   // ceil(nb / st_chunk_blocks)
+    { const int kbt = st_chunk_blocks(ti.type); ti.nch = (nb + kbt - 1) / kbt; }
   }
   return ti;
 }
@@ -746,6 +756,72 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
   const int n_vec = n_total & ~31;
   const int left = T - n_vec;                         // <= 31; <= 0 when the eval chunk extends past this token
   const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
+#ifndef CTB_ATTN_VP_SERIAL
+  {  // the channels of this warp (cc = warp, warp + NW, ...) side by side: one pass over the probabilities feeds all of them and
+     // their leftover chains (sequential double adds, ggml.c:2415-2418) overlap instead of running one after the other
+    constexpr int R = (ATTN_CH + NW - 1) / NW;
+    const uint16_t* vrow[R];
+    uint16_t vcur[R];
+    float s[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int cc = warp + r * NW;
+      s[r] = 0.f;
+      vrow[r] = nullptr;
+      vcur[r] = 0;
+      if (cc < ATTN_CH) {
+        const int iv = cc / g.cv;
+        const uint32_t n = seq0 + (uint32_t)(g.n_k + iv), slot = st_slot(n, S);
+        mbar_wait(&full_bar[slot], st_parity(n, S), 9, (int)n);
+        vrow[r] = (const uint16_t*)(ring + (size_t)slot * ST_SLOT + (size_t)(cc % g.cv) * g.nchv * 512);
+        vcur[r] = v16[cg * ATTN_CH + cc];
+      }
+    }
+    for (int ch = 0; ch * 256 < n_vec_eff; ch++) {
+      const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
+      const uint32_t pw[4] = {pp.x, pp.y, pp.z, pp.w};
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (warp + r * NW >= ATTN_CH) continue;
+        const uint4 vv = *(const uint4*)(vrow[r] + ch * 256 + lane * 8);
+        const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int t = ch * 256 + 32 * i + lane;
+          if (t < n_vec_eff) {
+            uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+            const uint16_t ph16 = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
+            if (t == pos) vh = vcur[r];
+            s[r] = __fmaf_rn(h2f(vh), h2f(ph16), s[r]);
+          }
+        }
+      }
+    }
+    double sumf[R];
+    float term[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      sumf[r] = (double)attn_reduce_f32x8(s[r]);
+      term[r] = 0.f;
+      if (left > 0 && warp + r * NW < ATTN_CH) {
+        const int t = n_vec + lane;
+        uint16_t vh = vrow[r][ch_left * 256 + lane * 8 + i_left];
+        const uint16_t ph16 = p16[ch_left * 256 + lane * 8 + i_left];
+        if (t == pos) vh = vcur[r];
+        term[r] = __fmul_rn(h2f(vh), h2f(ph16));
+      }
+    }
+    for (int l = 0; l < left; l++) {
+#pragma unroll
+      for (int r = 0; r < R; r++) sumf[r] += (double)__shfl_sync(0xffffffffu, term[r], l);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const int cc = warp + r * NW;
+      if (lane == 0 && cc < ATTN_CH) p.out[(size_t)h * hd + cg * ATTN_CH + cc] = (float)sumf[r];
+    }
+  }
+#else
   for (int cc = warp; cc < ATTN_CH; cc += NW) {
     const int c = cg * ATTN_CH + cc;
     const int iv = cc / g.cv;
@@ -781,6 +857,7 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
     }
     if (lane == 0) p.out[(size_t)h * hd + c] = (float)sumf;
   }
+#endif
   bar_sync<ST_BAR, ST_NT>();
   if (threadIdx.x < g.n_v) {
     const uint32_t n = seq0 + (uint32_t)(g.n_k + threadIdx.x);

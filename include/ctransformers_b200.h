@@ -134,7 +134,8 @@ int ctb_ffn_gate(int type, const void* w1_blocks, const void* w3_blocks, const f
 /* ggml_get_rows on a quantized table (ggml.c:11615-11642). */
 /* How a K-quant mat-vec phase over nseg matrices (types[], rows[], all K wide) is cut up on a GPU with n_sm SMs — pure host
  * arithmetic, no device needed: first_tile[0..grid] = first 16-row tile of each CTA (byte-balanced), meta = {grid, ring slot
- * bytes, tiles alive per CTA (mailboxes), tiles, consumer warps per CTA, rows per tile, work items of the largest CTA}.  0 on success. */
+ * bytes, tiles alive per CTA (mailboxes), tiles, consumer warps per CTA, rows per tile, work items of the largest CTA,
+ * blocks per work item as Q4_K | Q5_K << 8 | Q6_K << 16}.  0 on success. */
 int ctb_matvec_partition(const int* types, const int* rows, int nseg, int K, int n_sm, int* first_tile, int* meta);
 
 int ctb_get_row(int type, const void* table_blocks, int K, int n_rows, int row, float* out);

@@ -7,7 +7,6 @@ import pytest
 
 Q4_K, Q5_K, Q6_K = 12, 13, 14
 COST = {Q4_K: 72, Q5_K: 88, Q6_K: 105}     # relative cost of a tile = bytes per row-block / 2
-CHUNK = {Q4_K: 4, Q5_K: 3, Q6_K: 2}        # blocks per work item (one ring slot)
 BLOCK_BYTES = {Q4_K: 144, Q5_K: 176, Q6_K: 210}
 
 SHAPES = [
@@ -34,7 +33,8 @@ def partition(lib, K, segs, n_sm=148):
     meta = (C.c_int * 8)()
     assert lib.ctb_matvec_partition(types, rows, len(segs), K, n_sm, first, meta) == 0
     grid = meta[0]
-    return list(first[:grid + 1]), dict(grid=grid, slot=meta[1], alive=meta[2], tiles=meta[3], warps=meta[4], rows_per_tile=meta[5], max_items=meta[6])
+    chunk = {Q4_K: meta[7] & 255, Q5_K: (meta[7] >> 8) & 255, Q6_K: (meta[7] >> 16) & 255}     # blocks per work item (a build knob)
+    return list(first[:grid + 1]), dict(grid=grid, slot=meta[1], alive=meta[2], tiles=meta[3], warps=meta[4], rows_per_tile=meta[5], max_items=meta[6], chunk=chunk)
 
 
 @pytest.mark.parametrize("name,K,segs", SHAPES, ids=[s[0] for s in SHAPES])
@@ -61,6 +61,8 @@ def test_work_items_fit_a_ring_slot_and_match_the_device_enumeration(lib, name, 
     library reports must equal the count from walking the tiles here."""
     first, m = partition(lib, K, segs)
     nb = K // 256
+    CHUNK = m["chunk"]
+    assert all(1 <= c <= 4 for c in CHUNK.values())
     for t in (Q4_K, Q5_K, Q6_K):
         assert 16 * BLOCK_BYTES[t] * CHUNK[t] <= m["slot"]
         assert (16 * BLOCK_BYTES[t]) % 16 == 0      # cp.async.bulk: 16-byte granularity
