@@ -777,7 +777,7 @@ void Engine::enqueue_ops(const std::vector<StepOp>& ops, const Phase* d_prog, co
       int j = i;
       while (j < n && capable(ops[j])) j++;
       mark(-1);
-      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, d_bounds + (size_t)i * (sm_count_ + 1), j - i, d_sync_));
+      CTB_CUDA(launch_step(step_shape_, stream_, d_prog + i, d_bounds + (size_t)i * (sm_count_ + 1), j - i, d_sync_, false, nullptr, tp_peer_));
       launches_per_step_++;
       mark(0);
       i = j;

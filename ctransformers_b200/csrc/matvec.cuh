@@ -175,8 +175,9 @@ __device__ __forceinline__ void load16_ll(const uint2* p, unsigned epoch, float 
   for (int j = 0; j < 8; j++) { u[2 * j] = __uint_as_float(q[j].x); u[2 * j + 1] = __uint_as_float(q[j].z); }
 }
 
+template <bool XC = false>
 __device__ __forceinline__ void load16x(const MVParams& xs, int base, int valid, float (&v)[16], unsigned epoch = 0) {
-  if (xs.x_mode == 2) {   // (K is a multiple of 256 and base of 16: a thread's 16 elements are all valid or all past the end)
+  if (XC && xs.x_mode == 2) {   // (K is a multiple of 256 and base of 16: a thread's 16 elements are all valid or all past the end)
     if (valid <= 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = 0.f;
@@ -211,7 +212,7 @@ __device__ __forceinline__ void preload_norm(NormPre& np, const float* nw, const
 }
 
 // The first NT threads of the CTA must call (named barrier BAR); each owns 16 consecutive elements per pass.
-template <int NT, int BAR>
+template <int NT, int BAR, bool XC = false>   // XC: the input may be a tensor-parallel exchange (x_mode 2); compiled out otherwise
 __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormPre& np, const float* nw, const float* nb_, float* norm_out, int norm_mode, float eps,
                                                   int K, int act, uint8_t* smem, double* red, bool write_norm, unsigned epoch = 0) {
   const int t = threadIdx.x, lane = t & 31;
@@ -219,7 +220,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
   // ---- statistics (fp64 sums like ggml.c:10700-10703 / 10630-10645; the order of a double sum does not reach the float result)
   float mean = 0.f, scale = 1.f;
   float v0[16];                          // pass 0's x stays in registers
-  load16x(xs, t * 16, K - t * 16, v0, epoch);
+  load16x<XC>(xs, t * 16, K - t * 16, v0, epoch);
   if (norm_mode == NORM_RMS) {
     double ss = 0.0;
     for (int ps = 0; ps < passes; ps++) {
@@ -229,7 +230,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       if (ps == 0) {
 #pragma unroll
         for (int e = 0; e < 16; e++) v[e] = v0[e];
-      } else load16x(xs, base, K - base, v, epoch);
+      } else load16x<XC>(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) ss += (double)__fmul_rn(v[e], v[e]);
     }
@@ -242,7 +243,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       const int base = (ps * NT + t) * 16;
       if ((base & ~511) >= K) continue;
       float v[16];
-      load16x(xs, base, K - base, v, epoch);
+      load16x<XC>(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) s1 += (double)v[e];
     }
@@ -253,7 +254,7 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
       const int base = (ps * NT + t) * 16;
       if ((base & ~511) >= K) continue;
       float v[16];
-      load16x(xs, base, K - base, v, epoch);
+      load16x<XC>(xs, base, K - base, v, epoch);
 #pragma unroll
       for (int e = 0; e < 16; e++) { const float d = (base + e < K) ? __fsub_rn(v[e], mean) : 0.f; s2 += (double)__fmul_rn(d, d); }
     }
@@ -266,9 +267,6 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
   const size_t off = ((size_t)K + 15) & ~(size_t)15;
   float* dd = (float*)(smem + off);
   int16_t* bs = (int16_t*)(smem + off + q8k_d_bytes(K));
-#ifndef CTB_STAGE_SERIAL
-  float vn[16];                             // the next pass's x, requested before this pass is processed (L2 round trips overlap)
-#endif
   for (int ps = 0; ps < passes; ps++) {
     const int base = (ps * NT + t) * 16;
     const int valid = K - base;
@@ -277,21 +275,8 @@ __device__ __forceinline__ void stage_activation(const MVParams& xs, const NormP
     if (ps == 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) v[e] = v0[e];
-    } else {
-#ifndef CTB_STAGE_SERIAL
-#pragma unroll
-      for (int e = 0; e < 16; e++) v[e] = vn[e];
-#else
-      load16x(xs, base, valid, v, epoch);
-#endif
-    }
-#ifndef CTB_STAGE_SERIAL
-    {
-      const int nbase = ((ps + 1) * NT + t) * 16;
-      if (ps + 1 < passes && (nbase & ~511) < K) load16x(xs, nbase, K - nbase, vn, epoch);
-    }
-#endif
-    if (write_norm && xs.x_mode == 2 && xs.sum_out && valid > 0) {
+    } else load16x<XC>(xs, base, valid, v, epoch);
+    if (XC && write_norm && xs.x_mode == 2 && xs.sum_out && valid > 0) {
 #pragma unroll
       for (int e = 0; e < 16; e++) if (e < valid) xs.sum_out[base + e] = v[e];
     }

@@ -388,7 +388,7 @@ template <> struct StTraits<GT_Q6_K> { static constexpr int KB = CTB_CHUNK_Q6, B
 // One work item: blocks [b0, b0 + nblk) of the 16-row tile whose pieces lie in `slot`.  Integer work first (the slot is
 // released as soon as the last weight word has been read), then the ordered fp32 fold: state in from the mailbox unless this
 // is the tile's first chunk, blocks folded in order, state out unless it is the last chunk — then hsum_float_8 and the epilogue.
-template <int TYPE>
+template <int TYPE, bool XC>
 __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_bar, int nblk, int b0, int kc, bool last, const StAct& a, int lane,
                                          volatile float* mail, volatile int* flag, const MVSeg& sg, const MVParams& p, int row0) {
   constexpr int KB = StTraits<TYPE>::KB, BB = StTraits<TYPE>::BB, NM = StTraits<TYPE>::NM;
@@ -466,7 +466,7 @@ __device__ __forceinline__ void run_item(const uint8_t* slot, uint64_t* empty_ba
   if (t < 2) {
     const int row = row0 + g + 8 * t;
     if (row < sg.w.M) {
-      if (a.xc) {   // tensor-parallel partial sum: {value (+ residual on the rank that carries it), exchange number} to every rank
+      if (XC && a.xc) {   // tensor-parallel partial sum: {value (+ residual on the rank that carries it), exchange number} to every rank
         float v = t ? out[1] : out[0];
         if (sg.epi == EPI_ADD) v = __fadd_rn(v, __ldcg(sg.res + row));
         const XchgParams& xc = *a.xc;
@@ -581,7 +581,7 @@ __device__ __forceinline__ TileInfo tile_info(const TileSpace& ts, const MVParam
     ti.seg = ts.locate(tl);
     ti.til = tl;
     ti.type = ti.seg == 0 ? p.seg[0].w.type : (ti.seg == 1 ? p.seg[1].w.type : p.seg[2].w.type);
-    { const int kbt = st_chunk_blocks(ti.type); ti.nch = (nb + kbt - 1) / kbt; }
+    ti.nch = ti.type == GT_Q4_K ? (nb + CTB_CHUNK_Q4 - 1) / CTB_CHUNK_Q4 : (ti.type == GT_Q5_K ? (nb + CTB_CHUNK_Q5 - 1) / CTB_CHUNK_Q5 : (nb + CTB_CHUNK_Q6 - 1) / CTB_CHUNK_Q6);   // ceil(nb / st_chunk_blocks): constant divisors
   }
   return ti;
 }
@@ -756,72 +756,6 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
   const int n_vec = n_total & ~31;
   const int left = T - n_vec;                         // <= 31; <= 0 when the eval chunk extends past this token
   const int ch_left = n_vec >> 8, i_left = (n_vec & 255) >> 5;
-#ifndef CTB_ATTN_VP_SERIAL
-  {  // the channels of this warp (cc = warp, warp + NW, ...) side by side: one pass over the probabilities feeds all of them and
-     // their leftover chains (sequential double adds, ggml.c:2415-2418) overlap instead of running one after the other
-    constexpr int R = (ATTN_CH + NW - 1) / NW;
-    const uint16_t* vrow[R];
-    uint16_t vcur[R];
-    float s[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int cc = warp + r * NW;
-      s[r] = 0.f;
-      vrow[r] = nullptr;
-      vcur[r] = 0;
-      if (cc < ATTN_CH) {
-        const int iv = cc / g.cv;
-        const uint32_t n = seq0 + (uint32_t)(g.n_k + iv), slot = st_slot(n, S);
-        mbar_wait(&full_bar[slot], st_parity(n, S), 9, (int)n);
-        vrow[r] = (const uint16_t*)(ring + (size_t)slot * ST_SLOT + (size_t)(cc % g.cv) * g.nchv * 512);
-        vcur[r] = v16[cg * ATTN_CH + cc];
-      }
-    }
-    for (int ch = 0; ch * 256 < n_vec_eff; ch++) {
-      const uint4 pp = *(const uint4*)(p16 + ch * 256 + lane * 8);
-      const uint32_t pw[4] = {pp.x, pp.y, pp.z, pp.w};
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (warp + r * NW >= ATTN_CH) continue;
-        const uint4 vv = *(const uint4*)(vrow[r] + ch * 256 + lane * 8);
-        const uint32_t vw[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const int t = ch * 256 + 32 * i + lane;
-          if (t < n_vec_eff) {
-            uint16_t vh = (uint16_t)((vw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
-            const uint16_t ph16 = (uint16_t)((pw[i >> 1] >> ((i & 1) * 16)) & 0xffff);
-            if (t == pos) vh = vcur[r];
-            s[r] = __fmaf_rn(h2f(vh), h2f(ph16), s[r]);
-          }
-        }
-      }
-    }
-    double sumf[R];
-    float term[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      sumf[r] = (double)attn_reduce_f32x8(s[r]);
-      term[r] = 0.f;
-      if (left > 0 && warp + r * NW < ATTN_CH) {
-        const int t = n_vec + lane;
-        uint16_t vh = vrow[r][ch_left * 256 + lane * 8 + i_left];
-        const uint16_t ph16 = p16[ch_left * 256 + lane * 8 + i_left];
-        if (t == pos) vh = vcur[r];
-        term[r] = __fmul_rn(h2f(vh), h2f(ph16));
-      }
-    }
-    for (int l = 0; l < left; l++) {
-#pragma unroll
-      for (int r = 0; r < R; r++) sumf[r] += (double)__shfl_sync(0xffffffffu, term[r], l);
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-      const int cc = warp + r * NW;
-      if (lane == 0 && cc < ATTN_CH) p.out[(size_t)h * hd + cg * ATTN_CH + cc] = (float)sumf[r];
-    }
-  }
-#else
   for (int cc = warp; cc < ATTN_CH; cc += NW) {
     const int c = cg * ATTN_CH + cc;
     const int iv = cc / g.cv;
@@ -857,7 +791,6 @@ __device__ __forceinline__ void st_attn_task(const AttnParams& p, uint8_t* smem,
     }
     if (lane == 0) p.out[(size_t)h * hd + c] = (float)sumf;
   }
-#endif
   bar_sync<ST_BAR, ST_NT>();
   if (threadIdx.x < g.n_v) {
     const uint32_t n = seq0 + (uint32_t)(g.n_k + threadIdx.x);
@@ -916,15 +849,18 @@ __device__ __forceinline__ void st_producer(const StepArgs& args, uint8_t* ring,
 }
 
 // Consumer side of one mat-vec phase.  `seq` is the running item number (identical in every warp and in the producer).
+// XC: the build of the kernel that can exchange partial vectors between ranks (tensor-parallel mode); the single-GPU build
+// carries none of that code.
+template <bool XC>
 __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& np, uint8_t* ring, uint8_t* act_smem, double* red, uint64_t* full_bar, uint64_t* empty_bar,
                                                 float (*mailbox)[ST_STATE * 32], int* flags, uint32_t S, uint32_t& seq, const int* tb, unsigned long long* tr,
                                                 unsigned xc_base) {
   const MVParams& p = ph.mv;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned epoch = xc_base + (unsigned)ph.xc.index + 1u;   // number of the exchange this phase consumes / produces (if any)
-  stage_activation<ST_NT, ST_BAR>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0, epoch);
+  const unsigned epoch = XC ? xc_base + (unsigned)ph.xc.index + 1u : 0u;   // number of the exchange this phase consumes / produces (if any)
+  stage_activation<ST_NT, ST_BAR, XC>(p, np, p.norm_w, p.norm_b, p.norm_out, p.norm_mode, p.eps, p.K, ACT_Q8_K, act_smem, red, blockIdx.x == 0, epoch);
   StAct a = st_act_extras<ST_NT, ST_BAR>(act_smem, p.K, ph.q6 != 0);
-  a.xc = ph.xc.role == 2 ? &ph.xc : nullptr;
+  a.xc = XC && ph.xc.role == 2 ? &ph.xc : nullptr;
   a.epoch = epoch;
   if (tr && threadIdx.x == 0) tr[1] = globaltimer_ns();
   bool first_item = tr != nullptr && threadIdx.x == 0;
@@ -963,9 +899,9 @@ __device__ __forceinline__ void st_matvec_phase(const Phase& ph, const NormPre& 
         volatile float* mail = mailbox[j];
         volatile int* flag = flags + j;
         const bool last = kc == nch - 1;
-        if (type == GT_Q4_K) run_item<GT_Q4_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
-        else if (type == GT_Q6_K) run_item<GT_Q6_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
-        else run_item<GT_Q5_K>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+        if (type == GT_Q4_K) run_item<GT_Q4_K, XC>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+        else if (type == GT_Q6_K) run_item<GT_Q6_K, XC>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
+        else run_item<GT_Q5_K, XC>(sp, &empty_bar[slot], nblk, b0, kc, last, a, lane, mail, flag, sg, p, til * ST_ROWS);
       }
       seq += (uint32_t)cnt;
     }
@@ -1001,6 +937,7 @@ __device__ __forceinline__ void st_pick_phase(const PickParams& pk, float* bv, i
   }
 }
 
+template <bool XC>
 static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_constant__ StepArgs args) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[ST_MAX_SLOTS];
@@ -1028,7 +965,7 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
   }
   const unsigned G = gridDim.x;
   uint32_t seq = 0;
-  const unsigned xc_base = ld_relaxed_u32(args.sync + 2);   // (changes only after every CTA has left its last barrier)
+  const unsigned xc_base = XC ? ld_relaxed_u32(args.sync + 2) : 0u;   // (changes only after every CTA has left its last barrier)
   unsigned xc_done = 0;
   // descriptor of phase ip -> ph_s[ip & 1]; issued one phase ahead so that no global round trip sits on the phase boundary
   auto fetch_phase = [&](int ip) {
@@ -1070,10 +1007,10 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     NormPre np;
     if (ph.kind == PH_MATVEC) preload_norm(np, ph.mv.norm_w, ph.mv.norm_b, ph.mv.norm_mode, ph.mv.K);
     if (tr && threadIdx.x == 0) tr[0] = globaltimer_ns();
-    if (ph.kind == PH_MATVEC && ph.xc.role == 1) xc_done++;
+    if (XC && ph.kind == PH_MATVEC && ph.xc.role == 1) xc_done++;
     if (ph.kind == PH_MATVEC) {
       // (the tile bounds were written by threads 0/1 above; the barriers inside the activation staging order them)
-      st_matvec_phase(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)(args.n_slots / ST_W), seq, &tb_s[ip & 1][0], tr, xc_base);
+      st_matvec_phase<XC>(ph, np, ring, act_smem, red, full_bar, empty_bar, mailbox, flags, (uint32_t)(args.n_slots / ST_W), seq, &tb_s[ip & 1][0], tr, xc_base);
     } else if (ph.kind == PH_ATTN) {
       const int n_cg = ph.at.hd / ATTN_CH, n_tasks = ph.at.n_head * n_cg;
       if (ph.q6) {
@@ -1109,7 +1046,7 @@ static __global__ void __launch_bounds__(ST_THREADS, 1) k_step(const __grid_cons
     if (atomicAdd(args.sync + 1, 1u) == G - 1) {   // every CTA is past its last barrier: re-arm for the next launch
       args.sync[0] = 0u;
       args.sync[1] = 0u;
-      args.sync[2] = xc_base + xc_done;
+      if (XC) args.sync[2] = xc_base + xc_done;
       __threadfence();
     }
   }
@@ -1173,7 +1110,7 @@ inline Phase matvec_phase(const MVParams& p) {
 
 static inline size_t step_max_dyn_smem() {
   cudaFuncAttributes fa{};
-  if (cudaFuncGetAttributes(&fa, k_step) != cudaSuccess) return 0;
+  if (cudaFuncGetAttributes(&fa, k_step<true>) != cudaSuccess) return 0;   // (the two builds share their static shared memory)
   int dev = 0, optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -1181,10 +1118,13 @@ static inline size_t step_max_dyn_smem() {
 }
 // point the kernels' watchdog at 4 ints of host-mapped memory (each translation unit has its own copy of the symbol)
 static inline cudaError_t st_set_debug_words(int* dev_ptr) { return cudaMemcpyToSymbol(g_st_dbg, &dev_ptr, sizeof(int*)); }
-static inline cudaError_t step_set_smem_limit(size_t bytes) { return cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); }
+static inline cudaError_t step_set_smem_limit(size_t bytes) {
+  const cudaError_t e = cudaFuncSetAttribute(k_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e != cudaSuccess ? e : cudaFuncSetAttribute(k_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
 
 static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, const Phase* d_prog, const int* d_bounds, int n_phases, unsigned* d_sync, bool pdl = false,
-                                      unsigned long long* trace = nullptr) {
+                                      unsigned long long* trace = nullptr, bool xchg = false) {
   StepArgs a;
   a.prog = d_prog; a.bounds = d_bounds; a.n_phases = n_phases; a.n_slots = L.n_slots; a.sync = d_sync; a.trace = trace;
   cudaLaunchConfig_t cfg{};
@@ -1193,7 +1133,7 @@ static inline cudaError_t launch_step(const StepLaunch& L, cudaStream_t st, cons
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_step, a);
+  return xchg ? cudaLaunchKernelEx(&cfg, k_step<true>, a) : cudaLaunchKernelEx(&cfg, k_step<false>, a);
 }
 
 }  // namespace ctb

@@ -21,6 +21,7 @@ if [ $rc -ne 0 ] && [ -f $L/libctransformers_base.so ]; then
   timeout -k 5 300 python -m pytest tests/test_model_gpu.py -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/${tag}_pytest_gpu_base.txt
 fi
 echo "== bench (default: 192 steps)"; timeout -k 5 400 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err; cut -c1-300 gpurun_out/${tag}_bench_n1.json
+echo "== bench (driver's flags)"; timeout -k 5 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/${tag}_bench_n1_s20.json 2>/dev/null; cut -c1-200 gpurun_out/${tag}_bench_n1_s20.json
 echo "== reference arm"; timeout -k 5 400 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/${tag}_bench_reference.json 2>/dev/null; cut -c1-200 gpurun_out/${tag}_bench_reference.json
 echo "== prefill2048"; timeout -k 5 300 python bench.py --workload prefill2048 --steps 3 > gpurun_out/${tag}_bench_prefill2048.json 2>/dev/null; cut -c1-200 gpurun_out/${tag}_bench_prefill2048.json
 echo "== trace"; timeout -k 5 200 python tools/trace_step.py gpurun_out/${tag}_trace_step.json > gpurun_out/${tag}_trace_step.txt 2>&1; tail -12 gpurun_out/${tag}_trace_step.txt
