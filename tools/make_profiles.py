@@ -68,6 +68,7 @@ md = [f"# {tag}: warp-stall sampling and instruction mix per captured launch (nc
 evidence = []
 best_i = 0.0
 seen = collections.Counter()
+done = set()
 for blk in blocks:
     lines = blk.splitlines()
     name = lines[0].strip('",')
@@ -77,6 +78,9 @@ for blk in blocks:
     num = lambda x: float(x) if x not in ("", None) else 0.0
     tot_i = sum(num(r[ix["Instructions Executed"]]) for r in data)
     tot_s = sum(num(r[ix["# Samples"]]) for r in data)
+    if (name, tot_i, tot_s) in done:   # the source page lists every launch once per view
+        continue
+    done.add((name, tot_i, tot_s))
     seen[name] += 1
     md += [f"## {name}  (capture {seen[name]}: {tot_i:.0f} warp instructions, {tot_s:.0f} samples, {len(data)} SASS lines)", ""]
     stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
