@@ -29,6 +29,15 @@ __device__ __forceinline__ float dequant_elem(int type, const uint8_t* row, int 
       const int nib = r < 16 ? (byte & 0xF) : (byte >> 4);
       return __fmul_rn((float)(nib - 8), d);
     }
+    case GT_Q5_0: {   // dequantize_row_q5_0 (ggml.c:1559-1582): block = d, qh[4], qs[16]
+      const uint8_t* blk = row + (size_t)(e >> 5) * 22;
+      const int r = e & 31;
+      const float d = h2f((uint16_t)(blk[0] | (blk[1] << 8)));
+      const uint32_t qh = (uint32_t)blk[2] | ((uint32_t)blk[3] << 8) | ((uint32_t)blk[4] << 16) | ((uint32_t)blk[5] << 24);
+      const int byte = blk[6 + (r & 15)];
+      const int nib = r < 16 ? (byte & 0xF) : (byte >> 4);
+      return __fmul_rn((float)((nib | (int)(((qh >> r) & 1u) << 4)) - 16), d);
+    }
     case GT_Q8_0: {
       const uint8_t* blk = row + (size_t)(e >> 5) * 34;
       const float d = h2f((uint16_t)(blk[0] | (blk[1] << 8)));

@@ -10,6 +10,7 @@
 //
 //   type   plane qs (per row)          plane qh (per row)   plane sc (per row)               plane d (per row)
 //   Q4_0   nb x 16 B nibbles           -                    -                                 nb x fp16
+//   Q5_0   nb x 16 B nibbles           nb x 4 B fifth bits  -                                 nb x fp16
 //   Q8_0   nb x 32 B int8              -                    -                                 nb x fp16
 //   F16    K x 2 B                     -                    -                                 -
 //   F32    K x 4 B                     -                    -                                 -
@@ -24,7 +25,7 @@
 
 namespace ctb {
 
-enum : int { GT_F32 = 0, GT_F16 = 1, GT_Q4_0 = 2, GT_Q8_0 = 8, GT_Q4_K = 12, GT_Q5_K = 13, GT_Q6_K = 14 };
+enum : int { GT_F32 = 0, GT_F16 = 1, GT_Q4_0 = 2, GT_Q5_0 = 6, GT_Q8_0 = 8, GT_Q4_K = 12, GT_Q5_K = 13, GT_Q6_K = 14 };
 
 struct DevMat {
   int type = -1;
@@ -43,7 +44,7 @@ __host__ __device__ inline bool type_is_kquant(int t) { return t == GT_Q4_K || t
 enum : int { ACT_Q8_K = 0, ACT_Q8_0 = 1, ACT_F16 = 2, ACT_F32 = 3 };
 __host__ __device__ inline int act_format_for(int t) {
   if (type_is_kquant(t)) return ACT_Q8_K;
-  if (t == GT_Q4_0 || t == GT_Q8_0) return ACT_Q8_0;
+  if (t == GT_Q4_0 || t == GT_Q5_0 || t == GT_Q8_0) return ACT_Q8_0;
   if (t == GT_F16) return ACT_F16;
   return ACT_F32;
 }

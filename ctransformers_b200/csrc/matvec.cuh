@@ -400,6 +400,30 @@ __device__ __forceinline__ float dot_q40(const DevMat& w, int row, const ActView
   return group_hsum8(acc);
 }
 
+// Q5_0 (ggml.c:2983-3005): the nibble as for Q4_0 plus the fifth bit from qh (bit j = element j): the AVX2 kernel ORs 0xF0 into
+// the bytes whose bit is CLEAR, i.e. the int8 value is q5 - 16; then the same s8·s8 dot, fmadd and hsum as Q4_0.
+__device__ __forceinline__ float dot_q50(const DevMat& w, int row, const ActView& a, int l) {
+  const int nb = w.nb;
+  const uint8_t* qrow = w.qs + (size_t)row * nb * 16 + (l & 3) * 4;
+  const uint32_t* hrow = (const uint32_t*)w.qh + (size_t)row * nb;
+  const uint16_t* drow = w.d + (size_t)row * nb;
+  const int shift = (l >> 2) * 4;
+  float acc = 0.f;
+#pragma unroll 8
+  for (int b = 0; b < nb; b++) {
+    const uint32_t q = (uint32_t)__ldg((const int*)(qrow + (size_t)b * 16));
+    const uint32_t h4 = (__ldg(hrow + b) >> (4 * l)) & 0xfu;               // fifth bits of elements 4l..4l+3
+    const float dw = h2f(__ldg(drow + b));
+    const int aw = *(const int*)(a.qs + b * 32 + l * 4);
+    const float yd = a.d[b];
+    const uint32_t nib = (q >> shift) & 0x0f0f0f0fu;
+    const uint32_t set = (h4 * 0x00204081u) & 0x01010101u;                   // bit k of h4 -> bit 0 of byte k
+    const uint32_t bx = nib | ((set ^ 0x01010101u) * 0xf0u);                 // per byte: nibble - 16 when the bit is clear
+    acc = __fmaf_rn(__fmul_rn(dw, yd), (float)__dp4a((int)bx, aw, 0), acc);
+  }
+  return group_hsum8(acc);
+}
+
 __device__ __forceinline__ float dot_q80(const DevMat& w, int row, const ActView& a, int l) {
   const int nb = w.nb;
   const uint8_t* qrow = w.qs + (size_t)row * nb * 32 + l * 4;
@@ -416,7 +440,7 @@ __device__ __forceinline__ float dot_q80(const DevMat& w, int row, const ActView
 }
 
 __device__ __forceinline__ float dot_legacy(const DevMat& w, int row, const ActView& a, int l) {
-  return w.type == GT_Q4_0 ? dot_q40(w, row, a, l) : dot_q80(w, row, a, l);
+  return w.type == GT_Q4_0 ? dot_q40(w, row, a, l) : (w.type == GT_Q5_0 ? dot_q50(w, row, a, l) : dot_q80(w, row, a, l));
 }
 
 // GGML_F32x8_REDUCE over a warp that plays 4 accumulators x 8 lanes (lane = 8*j + l): (0+2),(1+3) -> (0+1) -> lo128+hi128 ->

@@ -61,12 +61,12 @@ OpsTables& tables() {
 size_t raw_row_bytes(int type, int K) {
   switch (type) {
     case GT_F32: return (size_t)K * 4; case GT_F16: return (size_t)K * 2;
-    case GT_Q4_0: return (size_t)K / 32 * 18; case GT_Q8_0: return (size_t)K / 32 * 34;
+    case GT_Q4_0: return (size_t)K / 32 * 18; case GT_Q5_0: return (size_t)K / 32 * 22; case GT_Q8_0: return (size_t)K / 32 * 34;
     case GT_Q4_K: return (size_t)K / 256 * 144; case GT_Q5_K: return (size_t)K / 256 * 176; case GT_Q6_K: return (size_t)K / 256 * 210;
   }
   throw std::runtime_error("unsupported ggml type " + std::to_string(type));
 }
-int block_elems(int type) { return type_is_kquant(type) ? 256 : (type == GT_Q4_0 || type == GT_Q8_0) ? 32 : 1; }
+int block_elems(int type) { return type_is_kquant(type) ? 256 : (type == GT_Q4_0 || type == GT_Q5_0 || type == GT_Q8_0) ? 32 : 1; }
 
 struct OwnedMat {
   DevMat m;

@@ -11,6 +11,7 @@ inline PlaneSizes plane_sizes(int type, int M, int nb, size_t raw_bytes) {
   const size_t nblk = (size_t)M * nb;
   switch (type) {
     case GT_Q4_0: return {nblk * 16, 0, 0, nblk * 2};
+    case GT_Q5_0: return {nblk * 16, nblk * 4, 0, nblk * 2};
     case GT_Q8_0: return {nblk * 32, 0, 0, nblk * 2};
     default: return {raw_bytes, 0, 0, 0};
   }
@@ -24,6 +25,10 @@ static __global__ void k_repack(int type, const uint16_t* __restrict__ raw, size
       case GT_Q4_0: {
         const size_t blk = idx / 9; const int o = (int)(idx % 9);
         if (o == 0) d[blk] = v; else qs[blk * 8 + (o - 1)] = v;
+      } break;
+      case GT_Q5_0: {   // 22 B: d, qh[4], qs[16]   (ggml.c:902-908)
+        const size_t blk = idx / 11; const int o = (int)(idx % 11);
+        if (o == 0) d[blk] = v; else if (o < 3) qh[blk * 2 + (o - 1)] = v; else qs[blk * 8 + (o - 3)] = v;
       } break;
       case GT_Q8_0: {
         const size_t blk = idx / 17; const int o = (int)(idx % 17);

@@ -20,8 +20,8 @@ from typing import Callable, Optional
 
 import numpy as np
 
-F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 8, 12, 13, 14
-BLOCK = {F32: (1, 4), F16: (1, 2), Q4_0: (32, 18), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210)}
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K = 0, 1, 2, 6, 8, 12, 13, 14
+BLOCK = {F32: (1, 4), F16: (1, 2), Q4_0: (32, 18), Q5_0: (32, 22), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210)}
 
 # gguf value types
 _U32, _F32, _STR, _ARR, _I32 = 4, 6, 8, 9, 5
@@ -103,6 +103,8 @@ def random_blocks(t, ne0, rows, sigma, rng):
     jitter = rng.uniform(0.7, 1.3, size=n)
     if t == Q4_0:      # w = d * (q - 8), q uniform 0..15 (std 4.61)
         out[:, 0:2] = _f16_bytes(sigma / 4.61 * jitter)
+    elif t == Q5_0:    # w = d * (q - 16), q uniform 0..31 (std 9.23)
+        out[:, 0:2] = _f16_bytes(sigma / 9.23 * jitter)
     elif t == Q8_0:    # w = d * q, q uniform int8 (std 73.9)
         out[:, 0:2] = _f16_bytes(sigma / 73.9 * jitter)
     elif t in (Q4_K, Q5_K):
@@ -225,7 +227,7 @@ FALCON_7B_SHAPED = FalconShape()
 def _type_plan(ftype):
     """(main type, more-bits type, output type, token_embd type) for a named ftype."""
     plan = {
-        "Q4_K_M": (Q4_K, Q6_K, Q6_K, Q4_K), "Q5_K_M": (Q5_K, Q6_K, Q6_K, Q5_K), "Q4_0": (Q4_0, Q4_0, Q6_K, Q4_0),
+        "Q4_K_M": (Q4_K, Q6_K, Q6_K, Q4_K), "Q5_K_M": (Q5_K, Q6_K, Q6_K, Q5_K), "Q4_0": (Q4_0, Q4_0, Q6_K, Q4_0), "Q5_0": (Q5_0, Q5_0, Q6_K, Q5_0),
         "Q8_0": (Q8_0, Q8_0, Q8_0, Q8_0), "Q6_K": (Q6_K, Q6_K, Q6_K, Q6_K), "Q4_K": (Q4_K, Q4_K, Q4_K, Q4_K),
         "Q5_K": (Q5_K, Q5_K, Q5_K, Q5_K), "F16": (F16, F16, F16, F16), "F32": (F32, F32, F32, F32),
     }

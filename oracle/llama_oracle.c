@@ -36,6 +36,7 @@ void orc_gelu(const float *x, float *y, int n);
 void orc_attn_head_n(const float *q, const uint16_t *kcache, size_t k_stride, const uint16_t *vcache, size_t v_stride,
                      int head_dim, int T, int n_total, float kq_scale, float *out);
 void orc_dequantize_row_q4_0(const void *vx, float *y, int k);
+void orc_dequantize_row_q5_0(const void *vx, float *y, int k);
 void orc_dequantize_row_q8_0(const void *vx, float *y, int k);
 void orc_dequantize_row_q4_K(const void *vx, float *y, int k);
 void orc_dequantize_row_q5_K(const void *vx, float *y, int k);
@@ -108,10 +109,11 @@ static void get_row(const orc_mat *t, int row, float *out) {
     const int K = t->K;
     if (t->type == 0) { memcpy(out, (const float *)t->data + (size_t)row * K, (size_t)K * 4); return; }
     if (t->type == 1) { const uint16_t *h = (const uint16_t *)t->data + (size_t)row * K; for (int i = 0; i < K; i++) out[i] = orc_fp16_to_fp32(h[i]); return; }
-    const int be = (t->type == 2 || t->type == 8) ? 32 : 256;
+    const int be = (t->type == 2 || t->type == 6 || t->type == 8) ? 32 : 256;
     const char *p = (const char *)t->data + (size_t)row * (K / be) * orc_sizeof_block(t->type);
     switch (t->type) {
         case 2: orc_dequantize_row_q4_0(p, out, K); break;
+        case 6: orc_dequantize_row_q5_0(p, out, K); break;
         case 8: orc_dequantize_row_q8_0(p, out, K); break;
         case 12: orc_dequantize_row_q4_K(p, out, K); break;
         case 13: orc_dequantize_row_q5_K(p, out, K); break;
@@ -140,7 +142,7 @@ static void matvec(const orc_mat *w, const float *x, float *y) {
 
 /* x = all-reduce over ranks of (rank 0: x + W_0 a_0; rank r: W_r a_r), W_r = columns [split[r], split[r+1]) of w (quantized types only) */
 static void matvec_row_parallel(const orc_mat *w, const float *a, float *x, int world, const int *split) {
-    const int be = (w->type == 2 || w->type == 8) ? 32 : 256, bb = orc_sizeof_block(w->type);
+    const int be = (w->type == 2 || w->type == 6 || w->type == 8) ? 32 : 256, bb = orc_sizeof_block(w->type);
     const size_t full_row = (size_t)(w->K / be) * bb;
     float *part = (float *)malloc(sizeof(float) * w->M);
     for (int r = 0; r < world; r++) {

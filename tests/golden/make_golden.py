@@ -22,7 +22,7 @@ sys.path.insert(0, str(HERE.parent))
 sys.path.insert(0, str(HERE.parent.parent))
 import modelcases  # noqa: E402
 import refs  # noqa: E402
-from refs import Q4_0, Q4_K, Q5_K, Q6_K, Q8_0, Q8_K, ptr  # noqa: E402
+from refs import Q4_0, Q4_K, Q5_0, Q5_K, Q6_K, Q8_0, Q8_K, ptr  # noqa: E402
 
 TEXTS = ["AI is going to", "  hello  world ", "héllo ☃ the", "", "theof and123", "a\nb\tc", "The people of the water were very little.",
          "that's what they'll've said", "12345 67", "\x00\x01"]
@@ -40,7 +40,7 @@ def kat_quant():
     w = (rng.standard_normal((m, k)) * 0.05).astype(np.float32)
     x = out["x_1024"]
     out["w_f32"] = w
-    for t, at in ((Q4_0, Q8_0), (Q8_0, Q8_0), (Q4_K, Q8_K), (Q5_K, Q8_K), (Q6_K, Q8_K)):
+    for t, at in ((Q4_0, Q8_0), (Q8_0, Q8_0), (Q4_K, Q8_K), (Q5_K, Q8_K), (Q6_K, Q8_K), (Q5_0, Q8_0)):   # (appended: earlier vectors keep their bytes)
         wq = refs.ref_quantize(t, w).reshape(m, -1)
         act = refs.ref_quantize_act(at, x)
         out[f"wq_{t}"] = wq
@@ -109,8 +109,11 @@ if __name__ == "__main__":
     import sys
     only = sys.argv[1:]          # python make_golden.py [model case ...]: regenerate only those model fixtures
     with tempfile.TemporaryDirectory() as tmp:
-        if only:
-            models(tmp, only)
+        if only:                 # "kat" regenerates kat_quant.npz (its vectors are appended per type, earlier ones keep their bytes)
+            if "kat" in only:
+                kat_quant()
+            if [o for o in only if o != "kat"]:
+                models(tmp, [o for o in only if o != "kat"])
         else:
             kat_quant()
             models(tmp)

@@ -14,6 +14,7 @@ CASES = {
     "falcon_tiny_q5km": ("falcon", synth.FalconShape(n_vocab=1024, n_embd=512, n_head=8, n_head_kv=1, n_ff=2048, n_layer=2, n_ctx_train=256), "Q5_K_M", 96),
     # wide enough that every mat-vec launch has many row tiles per CTA and QKV mixes Q4_K with Q6_K (layer 0 "use_more_bits")
     "llama_wide_q4km": ("llama", synth.LlamaShape(n_vocab=1536, n_embd=2048, n_head=16, n_head_kv=16, n_ff=5632, n_layer=2, n_ctx_train=256), "Q4_K_M", 96),
+    "llama_tiny_q5_0": ("llama", synth.LlamaShape(n_vocab=1024, n_embd=256, n_head=4, n_head_kv=4, n_ff=768, n_layer=2, n_ctx_train=256), "Q5_0", 64),
     "falcon_tiny_q4_0": ("falcon", synth.FalconShape(n_vocab=1024, n_embd=256, n_head=4, n_head_kv=1, n_ff=1024, n_layer=2, n_ctx_train=256), "Q4_0", 64),
 }
 PROMPT_LEN = 37   # with 24 new tokens the context reaches 61: the f16 dot of V·P then uses its SIMD lanes AND its scalar tail

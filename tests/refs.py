@@ -17,10 +17,10 @@ ORACLE_SO = ROOT / "oracle" / "_build" / "liboracle.so"
 REF_SO = ROOT / "oracle" / "_ref" / "libctransformers_ref.so"
 
 # ggml type ids (ggml.h enum ggml_type)
-F32, F16, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 1, 2, 8, 12, 13, 14, 15
-BLOCK = {Q4_0: (32, 18), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210), Q8_K: (256, 292),
+F32, F16, Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 1, 2, 6, 8, 12, 13, 14, 15
+BLOCK = {Q4_0: (32, 18), Q5_0: (32, 22), Q8_0: (32, 34), Q4_K: (256, 144), Q5_K: (256, 176), Q6_K: (256, 210), Q8_K: (256, 292),
          F32: (1, 4), F16: (1, 2)}
-TYPE_NAME = {Q4_0: "q4_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K"}
+TYPE_NAME = {Q4_0: "q4_0", Q5_0: "q5_0", Q8_0: "q8_0", Q4_K: "q4_K", Q5_K: "q5_K", Q6_K: "q6_K"}
 
 
 def row_bytes(t, k):
@@ -44,7 +44,7 @@ def oracle():
         o.orc_fp16_to_fp32.argtypes = [C.c_uint16]
         o.orc_fp32_to_fp16.restype = C.c_uint16
         o.orc_fp32_to_fp16.argtypes = [C.c_float]
-        for n in ("orc_vec_dot_q4_0_q8_0", "orc_vec_dot_q8_0_q8_0", "orc_vec_dot_q4_K_q8_K", "orc_vec_dot_q5_K_q8_K",
+        for n in ("orc_vec_dot_q4_0_q8_0", "orc_vec_dot_q5_0_q8_0", "orc_vec_dot_q8_0_q8_0", "orc_vec_dot_q4_K_q8_K", "orc_vec_dot_q5_K_q8_K",
                   "orc_vec_dot_q6_K_q8_K"):
             getattr(o, n).restype = C.c_float
             getattr(o, n).argtypes = [i, vp, vp]

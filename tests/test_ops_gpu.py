@@ -11,7 +11,7 @@ import pytest
 
 import refs
 from conftest import ptr
-from refs import F16, F32, Q4_0, Q4_K, Q5_K, Q6_K, Q8_0, Q8_K, row_bytes
+from refs import F16, F32, Q4_0, Q4_K, Q5_0, Q5_K, Q6_K, Q8_0, Q8_K, row_bytes
 
 pytestmark = pytest.mark.gpu
 
@@ -67,7 +67,7 @@ def _same_bits(got, want):
     assert not bad.any(), f"{int(bad.sum())} of {bad.size} values differ; max |diff| {np.abs(got - want).max():.3e}"
 
 
-@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q8_0])
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q5_0, Q8_0])
 @pytest.mark.parametrize("k,m", [(256, 3), (4096, 64), (11008, 33)])
 def test_mul_mat_vs_oracle(lib, t, k, m):
     o = refs.oracle()
@@ -179,7 +179,7 @@ def test_attention_bit_exact(lib, n_head, n_kv, hd, T, n_total):
     _same_bits(got, want)
 
 
-@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q4_0])
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q4_0, Q5_0])
 def test_ffn_gate_vs_oracle(lib, t):
     o = refs.oracle()
     k, m = 4096, 96
@@ -197,7 +197,7 @@ def test_ffn_gate_vs_oracle(lib, t):
     _same_bits(got, want)
 
 
-@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q8_0, F16, F32])
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q5_0, Q8_0, F16, F32])
 def test_get_row_bit_exact(lib, t):
     o = refs.oracle()
     k, rows = 512, 9
@@ -218,7 +218,7 @@ def test_get_row_bit_exact(lib, t):
 
 
 @pytest.mark.skipif(not refs.have_ref(), reason="oracle/_ref not present")
-@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q8_0])
+@pytest.mark.parametrize("t", [Q4_K, Q5_K, Q6_K, Q4_0, Q5_0, Q8_0])
 @pytest.mark.parametrize("k", [512, 1024, 2816])
 def test_mul_mat_real_quantized_weights(lib, t, k):
     """Weights produced by the reference's quantizer (all scale/min bit patterns occur, unlike the random-block generator)."""

@@ -8,10 +8,10 @@ import numpy as np
 import pytest
 
 import refs
-from refs import Q4_0, Q4_K, Q5_K, Q6_K, Q8_0, Q8_K, ptr, row_bytes
+from refs import Q4_0, Q4_K, Q5_0, Q5_K, Q6_K, Q8_0, Q8_K, ptr, row_bytes
 
 GOLD = Path(__file__).resolve().parent / "golden"
-TYPES = [(Q4_0, Q8_0), (Q8_0, Q8_0), (Q4_K, Q8_K), (Q5_K, Q8_K), (Q6_K, Q8_K)]
+TYPES = [(Q4_0, Q8_0), (Q5_0, Q8_0), (Q8_0, Q8_0), (Q4_K, Q8_K), (Q5_K, Q8_K), (Q6_K, Q8_K)]
 
 
 @pytest.fixture(scope="module")
@@ -110,7 +110,7 @@ class TestAgainstCompiledReference:
     def test_random_block_generator_is_valid_for_the_reference(self):
         """synth.random_blocks must produce blocks the reference dequantizes to finite, sensibly scaled weights."""
         from ctransformers_b200 import synth
-        for t in (Q4_0, Q8_0, Q4_K, Q5_K, Q6_K):
+        for t in (Q4_0, Q5_0, Q8_0, Q4_K, Q5_K, Q6_K):
             blocks = np.ascontiguousarray(synth.random_blocks(t, 1024, 8, 0.02, np.random.default_rng(t)))
             out = np.zeros(8 * 1024, np.float32)
             refs.ref_traits(t)["to_float"](ptr(blocks), ptr(out), out.size)
