@@ -32,7 +32,12 @@ static std::string watchdog_note() {
   const int* d = g_watchdog_words;
   if (!d) return " [no watchdog words]";
   if (d[0] == 0) return " [watchdog words clear]";
-  return " [step-kernel watchdog: wait " + std::to_string(d[0]) + " timed out in CTA " + std::to_string(d[1]) + ", aux " + std::to_string(d[2]) + ", thread " +
+  static const char* const what[] = {"?", "mbarrier", "grid barrier (aux = phase)", "fold hand-off flag (aux = chunk)", "producer: free weight slot (aux = item)",
+                                     "consumer: weight item (aux = item)", "producer: free K slot (attention)", "producer: free V slot (attention)",
+                                     "consumer: K item (attention)", "consumer: V item (attention)", "tensor-parallel exchange: a peer's element (aux = exchange number)", "?",
+                                     "prefill grid barrier (aux = phase)", "?", "prefill producer: free slot", "prefill consumer: weight item"};
+  const char* w = (d[0] > 0 && d[0] < (int)(sizeof(what) / sizeof(what[0]))) ? what[d[0]] : "?";
+  return " [step-kernel watchdog: wait " + std::to_string(d[0]) + " (" + w + ") timed out in CTA " + std::to_string(d[1]) + ", aux " + std::to_string(d[2]) + ", thread " +
          std::to_string(d[3]) + "]";
 }
 
