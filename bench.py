@@ -11,8 +11,8 @@ prefilled untimed, then W warm-up + K timed decode steps.
   value     device-timed: K steps replayed as CUDA graphs with the token fed back on the device (the pick phase), CUDA events on the
             launching stream, max over ranks; tokens/s summed over ranks (replicas: one sequence per GPU, weak scaling).  The
             logits stay on the device (no D2H inside this number; e2e below includes the step's result read-back)
-  e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, the sampler's device half
-            (penalty + top-k), its candidates D2H and the host draw inside the timed region
+  e2e       the same K steps through the public API (llm.eval([tok]) + llm.sample(top_k=1)): token H2D, the greedy pick made on
+            the device and its 8-byte read-back inside the timed region
   roofline  dominant kernel k_step, mat-vec phases (HBM-bound): the GGUF bytes of the weights the 129 mat-vec phases of a step read
             (4005.4 MB) ÷ the duration of a launch that holds exactly those phases (no attention / embedding / pick), measured live
             as a CUDA graph between CUDA events on the engine's stream; peak = MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram
@@ -309,7 +309,7 @@ def run_tp(args, path, rank, world, local, barrier, max_over_ranks, group):
                    "ctx": CTX, "prompt": PROMPT, "parallelism": f"tp{world} (column-parallel q/k/v/gate/up, row-parallel wo/down, {2 * shape.n_layer} all-reduces of {shape.n_embd} floats per token over NCCL)",
                    "l2": "each rank streams its GBs of weights per step: inputs exceed the 126 MB L2"},
         "clocks": clocks,
-        "e2e": {"value": steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 16 + 64 * 4, "d2h_bytes_per_step": 4 + 2064,
+        "e2e": {"value": steps / e2e_s, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 8,
                 "how": "llm.eval([tok]) + llm.sample(top_k=1) per step on every rank (same calls, same seed), wall clock, max over ranks"},
         "gpu_launches": launches * steps, "launches_per_token": launches, "comm_nranks": world,
         "roofline": {"bound": "hbm", "kernel": "k_step (all phases of a rank's step, exchanges included)", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -455,8 +455,8 @@ def main():
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16 + 64 * 4, "d2h_bytes_per_step": 4 + 2064,
-                "how": "llm.eval([tok]) + llm.sample(top_k=1) per step, wall clock between device syncs; per step: H2D {token, position} and the 64-token repetition window, D2H the look-ahead pick and the sampler's candidate block (logits stay on the device until llm.logits is asked for)",
+        "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 8,
+                "how": "llm.eval([tok]) + llm.sample(top_k=1, repetition_penalty=1.0) per step, wall clock between device syncs; per step: H2D {token, position, step, n_total} (16 B), D2H {arg-max of the logits, number of logits equal to it} (8 B) — a greedy sample() is answered by the pick the engine made on the device (a sampled one would add the 64-token window up and a 2 KB candidate block down); the logits stay on the device until llm.logits is asked for",
                 "lookahead_hits": int(llm.ctb_llm_speculative_hits()), "device_samples": device_samples},
         "value_excludes": "logits D2H (kept on the device; e2e includes the step's result read-back)",
         "gpu_launches": int(llm.ctb_llm_launches_per_token()) * steps,
